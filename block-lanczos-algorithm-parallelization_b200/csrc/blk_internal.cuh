@@ -1,0 +1,105 @@
+// blk_internal.cuh -- shared declarations of the CUDA implementation behind include/blk_lanczos.h
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include "modp.cuh"
+
+// ----------------------------------------------------------------------------------------------
+// Sparse operator layout ("interleaved chunk stream")
+//
+// One operator S (R x C) computes y(R x n) <- S x(C x n).  Its entries are stored row by row
+// (rows sorted, columns ascending inside a row); an empty row contributes one dummy entry
+// (col 0, val 0) so that every row owns at least one stored entry.  Each stored entry is a
+// uint2 {col | LAST<<31, val}; LAST marks the final entry of a row.
+//
+// The stream is cut into chunks of Q consecutive entries.  A lane-group (L lanes, L = n_pad/4
+// for n_pad >= 4, each lane owning V = n_pad/L columns) walks one chunk sequentially.  A warp
+// holds G = 32/L lane-groups, i.e. a tile of G*Q consecutive entries.  Inside a tile the entries
+// are interleaved, entry i of chunk g at offset i*G + g, so that at step i the warp's G groups
+// read G consecutive uint2 -- one coalesced request, every byte of the matrix is read exactly
+// once and no shared-memory staging is needed.
+//
+// Work is balanced by entries, not rows (power-law rows cost nothing extra).  Rows that
+// cross chunk borders are stitched with warp shuffles; rows that cross tile borders leave a
+// partial in y and one n-vector per tile in `whead`, completed by a small fix-up kernel.
+// ----------------------------------------------------------------------------------------------
+struct SpOp {
+        int64_t rows = 0;          // R: output rows (local rows of this rank)
+        int64_t cols = 0;          // C: input rows (global)
+        int64_t nnz = 0;           // real entries
+        int64_t stored = 0;        // nnz + empty-row dummies
+        int64_t ntiles = 0;        // warp tiles (stored padded up to ntiles*G*Q)
+        int Q = 0, G = 0;
+        uint2 *ent = nullptr;      // [ntiles*G*Q]
+        u32 *chunk_row = nullptr;  // [ntiles*G]  first row of the chunk | HEAD_OPEN<<31
+        u32 *tail_row = nullptr;   // [ntiles]    row left open at the end of the tile (started in it)
+        u32 *span = nullptr;       // [ntiles]    number of following tiles that finish that row (0: none)
+        u32 *whead = nullptr;      // [ntiles*n_pad] scratch: the tile's contribution to a row opened earlier
+        size_t bytes = 0;
+};
+
+// n x n working set of one iteration, resident on the device.  All matrices are stored with
+// leading dimension n_pad (zero padded) so the row kernels can use them directly.
+struct DevSmall {
+        int iters;        // the reference's n_iterations
+        int limit;        // blk_iterate: stop when iters == limit (<=0: no limit)
+        int stopped;      // semi_inverse returned 0 pivots
+        int halt;         // skip whole iterations (stopped or limit reached)
+        int do_ortho;     // set by the small kernel of the current iteration
+        int npiv;         // last semi_inverse return value
+        int bad_index;    // layout build: COO index out of range
+        int pad_;
+};
+
+struct Geometry {
+        int n = 0, np = 0;      // blocking factor and its power-of-two padding
+        int L = 0, V = 0, G = 0; // lanes per entry, u32 per lane, groups per warp
+};
+
+static inline Geometry make_geometry(int n)
+{
+        Geometry g;
+        g.n = n;
+        int np = 1;
+        while (np < n) np <<= 1;
+        g.np = np;
+        g.V = np < 4 ? np : 4;
+        g.L = np / g.V;
+        g.G = 32 / g.L;
+        return g;
+}
+
+// ---- launchers (each returns the number of kernels it launched) ---------------------------
+// layout_build.cu
+std::string build_operator(SpOp *op, const Geometry &geo, int chunk_len, int64_t rows, int64_t cols,
+                           int64_t row_lo, int64_t nnz, const int32_t *d_row, const int32_t *d_col,
+                           const u32 *d_val, u32 prime, cudaStream_t st);
+void free_operator(SpOp *op);
+
+// spmv.cu
+int launch_spmv(const SpOp &op, const Geometry &geo, const ModP &m, const u32 *x, u32 *y,
+                const DevSmall *state, cudaStream_t st);
+
+// dense.cu
+int dots_num_blocks(int64_t rows, int np);
+int launch_dots(const Geometry &geo, const ModP &m, int64_t rows, const u32 *v, const u32 *Av,
+                u32 *partials, int nblocks, const DevSmall *state, cudaStream_t st);
+// mats layout (u32, each np*np unless noted): [0] vtAv [1] vtAAv [2] winv [3] c [4] vtAvd [5] d (np)
+enum { MAT_VTAV = 0, MAT_VTAAV = 1, MAT_WINV = 2, MAT_C = 3, MAT_VTAVD = 4, MAT_D = 5, MAT_COUNT = 6 };
+// sums: if partials != nullptr the kernel adds `nblocks` partial blocks, else it reads the u64
+// array `sums` (2*np*np, e.g. after an all-reduce).  mode: 0 full iteration step (semi_inverse +
+// coefficients + flags), 1 only reduce dots into MAT_VTAV/MAT_VTAAV, 2 semi_inverse of MAT_VTAV
+// only, 3 coefficients from given MAT_D/MAT_WINV/MAT_VTAV/MAT_VTAAV.
+int launch_small(const Geometry &geo, const ModP &m, const u32 *partials, int nblocks, const u64 *sums,
+                 u32 *mats, DevSmall *state, int mode, cudaStream_t st);
+int launch_partials_to_sums(const Geometry &geo, const ModP &m, const u32 *partials, int nblocks,
+                            u64 *sums, const DevSmall *state, cudaStream_t st);
+int launch_ortho(const Geometry &geo, const ModP &m, int64_t rows, u32 *v, const u32 *Av, u32 *p,
+                 u32 *v_out, u32 *p_out, const u32 *mats, const DevSmall *state, int force,
+                 cudaStream_t st);
+// per-device one-time kernel attributes (call with the device current, outside stream capture)
+void dense_prepare(const Geometry &geo, const ModP &m);
+// n <-> n_pad repacking of row-major blocks (rows x n  <->  rows x np)
+int launch_pad_rows(const u32 *src, u32 *dst, int64_t rows, int n, int np, cudaStream_t st);
+int launch_unpad_rows(const u32 *src, u32 *dst, int64_t rows, int n, int np, cudaStream_t st);

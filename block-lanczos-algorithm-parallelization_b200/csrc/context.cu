@@ -1,0 +1,898 @@
+// context.cu -- implementation of the C ABI in include/blk_lanczos.h.
+//
+// The context owns what block_lanczos (sequential/lanczos_modp.c:585-669) owns on the host:
+// the matrix (as two GPU-resident operators S1, S2 instead of COO arrays) and the four vector
+// blocks v, tmp, Av, p.  blk_iterate enqueues the loop body (:635-656) as kernels on one
+// stream; the stop decision (:644,:649) and the iteration counter live on the device, so a
+// batch of iterations (optionally one CUDA graph per 16 iterations) runs without any host
+// round trip and freezes exactly at the iteration where semi_inverse finds no pivot.
+//
+// Multi-GPU (world > 1, one context per GPU/process): rows of the Lanczos vectors and of both
+// operators are sharded in contiguous, weight-balanced blocks.  Per iteration: all-gather v,
+// local S1, all-gather tmp, local S2, local dots, all-reduce of 2 n^2 u64 sums, redundant
+// semi_inverse, local orthogonalize.  Collectives go through NCCL (resolved with dlopen so the
+// library loads on machines without it); the reference's MPI version does the same steps with
+// hand-rolled Send/Recv reductions on a root (mpi/lanczos_modp.c:1088-1125, 1209-1256).
+#include <dlfcn.h>
+#include <nccl.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include "../../include/blk_lanczos.h"
+#include "blk_internal.cuh"
+
+static thread_local std::string g_err;
+
+static int fail(const std::string &msg)
+{
+        g_err = msg;
+        return 1;
+}
+
+#define CU(call)                                                                                   \
+        do {                                                                                       \
+                cudaError_t e_ = (call);                                                           \
+                if (e_ != cudaSuccess)                                                             \
+                        return fail(std::string(#call) + ": " + cudaGetErrorString(e_));           \
+        } while (0)
+
+// ---------------------------------------------------------------------------------- NCCL (dlopen)
+namespace {
+struct NcclApi {
+        void *lib = nullptr;
+        ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+        ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+        ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+        ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+        ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+        ncclResult_t (*GroupStart)() = nullptr;
+        ncclResult_t (*GroupEnd)() = nullptr;
+        const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+bool nccl_load(std::string *why)
+{
+        if (g_nccl.lib) return true;
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) { *why = std::string("cannot load NCCL: ") + dlerror(); return false; }
+#define SYM(field, name)                                                                           \
+        *(void **)(&g_nccl.field) = dlsym(h, name);                                                \
+        if (!g_nccl.field) { *why = std::string("NCCL symbol missing: ") + name; return false; }
+        SYM(GetUniqueId, "ncclGetUniqueId")
+        SYM(CommInitRank, "ncclCommInitRank")
+        SYM(CommDestroy, "ncclCommDestroy")
+        SYM(AllReduce, "ncclAllReduce")
+        SYM(Broadcast, "ncclBroadcast")
+        SYM(GroupStart, "ncclGroupStart")
+        SYM(GroupEnd, "ncclGroupEnd")
+        SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+        g_nccl.lib = h;
+        return true;
+}
+}  // namespace
+
+#define NC(call)                                                                                   \
+        do {                                                                                       \
+                ncclResult_t r_ = (call);                                                          \
+                if (r_ != ncclSuccess)                                                             \
+                        return fail(std::string(#call) + ": " + g_nccl.GetErrorString(r_));        \
+        } while (0)
+
+// ---------------------------------------------------------------------------------- context
+struct blk_ctx {
+        Geometry geo;
+        ModP m;
+        int device = 0, rank = 0, world = 1, right = 0;
+        int32_t nrows = 0, ncols = 0;
+        int64_t N = 0, Mc = 0;
+        std::vector<int64_t> n_off, m_off;      // row partition of the N and Mc dimensions
+        SpOp S1, S2;                            // tmp <- S1 v ; Av <- S2 tmp
+        u32 *v = nullptr, *tmp = nullptr;       // full length: N*np, Mc*np
+        u32 *Av = nullptr, *p = nullptr;        // local rows [n0,n1) * np
+        u32 *partials = nullptr, *mats = nullptr;
+        u64 *sums = nullptr;
+        DevSmall *state = nullptr, *h_state = nullptr;
+        int dots_blocks = 1;
+        cudaStream_t stream = nullptr;
+        bool own_stream = false;
+        ncclComm_t comm = nullptr;
+        // loop bookkeeping
+        int iters = 0, stopped = 0;
+        bool tmp_is_spmv = false;               // tmp rows [0,Mc) hold S1*v of the current v (stop case)
+        bool any_ortho = false;
+        // graphs
+        int use_graph = -1;
+        cudaGraphExec_t graph = nullptr;
+        static constexpr int GRAPH_ITERS = 16;
+        // profiling
+        bool profiling = false;
+        double ph_ms[BLK_PH_COUNT] = {0};
+        int64_t ph_launch[BLK_PH_COUNT] = {0};
+        int64_t launches = 0;
+        size_t block_bytes = 0;
+
+        int64_t n0() const { return n_off[rank]; }
+        int64_t n1() const { return n_off[rank + 1]; }
+        int64_t m0() const { return m_off[rank]; }
+        int64_t m1() const { return m_off[rank + 1]; }
+};
+
+namespace {
+
+struct EventTimer {
+        // records (phase, start, stop) triples on the stream; resolved after a sync
+        struct Rec { int ph; cudaEvent_t a, b; int launches; };
+        std::vector<Rec> recs;
+        void begin(blk_ctx *c, int ph)
+        {
+                Rec r; r.ph = ph; r.launches = 0;
+                cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+                cudaEventRecord(r.a, c->stream);
+                recs.push_back(r);
+        }
+        void end(blk_ctx *c, int launches)
+        {
+                recs.back().launches = launches;
+                cudaEventRecord(recs.back().b, c->stream);
+        }
+        void resolve(blk_ctx *c)
+        {
+                for (auto &r : recs) {
+                        float ms = 0;
+                        cudaEventElapsedTime(&ms, r.a, r.b);
+                        c->ph_ms[r.ph] += ms;
+                        c->ph_launch[r.ph] += r.launches;
+                        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+                }
+                recs.clear();
+        }
+};
+
+// weight-balanced contiguous partition of `dim` rows into `world` blocks
+std::vector<int64_t> partition_rows(const std::vector<u32> &cnt, int world)
+{
+        int64_t dim = (int64_t)cnt.size();
+        std::vector<int64_t> off(world + 1, 0);
+        long double total = 0;
+        for (int64_t r = 0; r < dim; r++) total += (long double)cnt[r] + 8.0L;
+        long double run = 0;
+        int k = 1;
+        for (int64_t r = 0; r < dim && k < world; r++) {
+                run += (long double)cnt[r] + 8.0L;
+                while (k < world && run >= total * k / world) off[k++] = r + 1;
+        }
+        while (k < world) off[k++] = dim;
+        off[world] = dim;
+        return off;
+}
+
+__global__ void k_count_rows(int64_t nnz, const int32_t *__restrict__ idx, int64_t dim, u32 *__restrict__ cnt)
+{
+        int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (s >= nnz) return;
+        int64_t r = idx[s];
+        if (r >= 0 && r < dim) atomicAdd(&cnt[r], 1u);
+}
+
+__global__ void k_select_range(int64_t nnz, const int32_t *__restrict__ key, const int32_t *__restrict__ other,
+                               const u32 *__restrict__ val, int64_t lo, int64_t hi, int32_t *__restrict__ okey,
+                               int32_t *__restrict__ oother, u32 *__restrict__ oval,
+                               unsigned long long *__restrict__ counter)
+{
+        int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (s >= nnz) return;
+        int64_t k = key[s];
+        if (k < lo || k >= hi) return;
+        unsigned long long pos = atomicAdd(counter, 1ull);
+        okey[pos] = (int32_t)k; oother[pos] = other[s]; oval[pos] = val[s];
+}
+
+inline unsigned nb(int64_t n) { return (unsigned)((n + 255) / 256); }
+
+int allgather_rows(blk_ctx *c, u32 *buf, const std::vector<int64_t> &off)
+{
+        NC(g_nccl.GroupStart());
+        for (int r = 0; r < c->world; r++) {
+                size_t cnt = (size_t)(off[r + 1] - off[r]) * c->geo.np;
+                u32 *ptr = buf + (size_t)off[r] * c->geo.np;
+                if (cnt) NC(g_nccl.Broadcast(ptr, ptr, cnt, ncclUint32, r, c->comm, c->stream));
+        }
+        NC(g_nccl.GroupEnd());
+        return 0;
+}
+
+// one iteration of the loop body, sequential/lanczos_modp.c:635-656
+int enqueue_iteration(blk_ctx *c, EventTimer *tm)
+{
+        const Geometry &g = c->geo;
+        const int np = g.np;
+        int k;
+        if (c->world > 1) {
+                if (tm) tm->begin(c, BLK_PH_EXCHANGE);
+                if (allgather_rows(c, c->v, c->n_off)) return 1;
+                if (tm) tm->end(c, 0);
+        }
+        if (tm) tm->begin(c, BLK_PH_SPMV1);
+        k = launch_spmv(c->S1, g, c->m, c->v, c->tmp + (size_t)c->m0() * np, c->state, c->stream);
+        c->launches += k;
+        if (tm) tm->end(c, k);
+        if (c->world > 1) {
+                if (tm) tm->begin(c, BLK_PH_EXCHANGE);
+                if (allgather_rows(c, c->tmp, c->m_off)) return 1;
+                if (tm) tm->end(c, 0);
+        }
+        if (tm) tm->begin(c, BLK_PH_SPMV2);
+        k = launch_spmv(c->S2, g, c->m, c->tmp, c->Av, c->state, c->stream);
+        c->launches += k;
+        if (tm) tm->end(c, k);
+
+        int64_t lrows = c->n1() - c->n0();
+        u32 *vloc = c->v + (size_t)c->n0() * np;
+        if (tm) tm->begin(c, BLK_PH_DOTS);
+        k = launch_dots(g, c->m, lrows, vloc, c->Av, c->partials, c->dots_blocks, c->state, c->stream);
+        c->launches += k;
+        if (tm) tm->end(c, k);
+        if (c->world > 1) {
+                if (tm) tm->begin(c, BLK_PH_EXCHANGE);
+                k = launch_partials_to_sums(g, c->m, c->partials, c->dots_blocks, c->sums, c->state, c->stream);
+                c->launches += k;
+                NC(g_nccl.AllReduce(c->sums, c->sums, (size_t)2 * np * np, ncclUint64, ncclSum, c->comm, c->stream));
+                if (tm) tm->end(c, k);
+                if (tm) tm->begin(c, BLK_PH_SMALL);
+                k = launch_small(g, c->m, nullptr, 0, c->sums, c->mats, c->state, 0, c->stream);
+        } else {
+                if (tm) tm->begin(c, BLK_PH_SMALL);
+                k = launch_small(g, c->m, c->partials, c->dots_blocks, nullptr, c->mats, c->state, 0, c->stream);
+        }
+        c->launches += k;
+        if (tm) tm->end(c, k);
+        if (tm) tm->begin(c, BLK_PH_ORTHO);
+        k = launch_ortho(g, c->m, lrows, vloc, c->Av, c->p, vloc, c->p, c->mats, c->state, 0, c->stream);
+        c->launches += k;
+        if (tm) tm->end(c, k);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(e));
+        return 0;
+}
+
+int push_state(blk_ctx *c)
+{
+        CU(cudaMemcpyAsync(c->state, c->h_state, sizeof(DevSmall), cudaMemcpyHostToDevice, c->stream));
+        return 0;
+}
+int pull_state(blk_ctx *c)
+{
+        CU(cudaMemcpyAsync(c->h_state, c->state, sizeof(DevSmall), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        return 0;
+}
+
+// host block (rows x n, row-major) -> device block with leading dimension np
+int upload_rows(blk_ctx *c, u32 *dst, const u32 *src_host, int64_t rows)
+{
+        const int n = c->geo.n, np = c->geo.np;
+        if (rows == 0) return 0;
+        if (n == np) {
+                CU(cudaMemcpyAsync(dst, src_host, sizeof(u32) * (size_t)rows * n, cudaMemcpyHostToDevice, c->stream));
+                CU(cudaStreamSynchronize(c->stream));
+                return 0;
+        }
+        u32 *stage = nullptr;
+        CU(cudaMalloc(&stage, sizeof(u32) * (size_t)rows * n));
+        CU(cudaMemcpyAsync(stage, src_host, sizeof(u32) * (size_t)rows * n, cudaMemcpyHostToDevice, c->stream));
+        c->launches += launch_pad_rows(stage, dst, rows, n, np, c->stream);
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(stage);
+        return 0;
+}
+int download_rows(blk_ctx *c, u32 *dst_host, const u32 *src, int64_t rows)
+{
+        const int n = c->geo.n, np = c->geo.np;
+        if (rows == 0) return 0;
+        if (n == np) {
+                CU(cudaMemcpyAsync(dst_host, src, sizeof(u32) * (size_t)rows * n, cudaMemcpyDeviceToHost, c->stream));
+                CU(cudaStreamSynchronize(c->stream));
+                return 0;
+        }
+        u32 *stage = nullptr;
+        CU(cudaMalloc(&stage, sizeof(u32) * (size_t)rows * n));
+        c->launches += launch_unpad_rows(src, stage, rows, n, np, c->stream);
+        CU(cudaMemcpyAsync(dst_host, stage, sizeof(u32) * (size_t)rows * n, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(stage);
+        return 0;
+}
+
+void destroy_graph(blk_ctx *c)
+{
+        if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
+}
+
+int build_graph(blk_ctx *c)
+{
+        cudaGraph_t g = nullptr;
+        CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        int64_t before = c->launches;
+        int rc = 0;
+        for (int i = 0; i < blk_ctx::GRAPH_ITERS && !rc; i++) rc = enqueue_iteration(c, nullptr);
+        c->launches = before;       // counted when the graph is launched
+        cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+        if (rc) { if (g) cudaGraphDestroy(g); return 1; }
+        if (e != cudaSuccess) return fail(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&c->graph, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return fail(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+        return 0;
+}
+
+int kernels_per_iteration(const blk_ctx *c) { return c->world > 1 ? 8 : 7; }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------- C ABI
+extern "C" {
+
+int blk_abi_version(void) { return BLK_ABI_VERSION; }
+
+const char *blk_last_error(void) { return g_err.c_str(); }
+
+int blk_device_count(int *count)
+{
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess) { *count = 0; return fail(std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e)); }
+        *count = n;
+        return 0;
+}
+
+int blk_nccl_unique_id(void *id_out)
+{
+        std::string why;
+        if (!nccl_load(&why)) return fail(why);
+        ncclUniqueId id;
+        NC(g_nccl.GetUniqueId(&id));
+        static_assert(sizeof(ncclUniqueId) == BLK_NCCL_ID_BYTES, "ncclUniqueId size");
+        memcpy(id_out, &id, sizeof(id));
+        return 0;
+}
+
+int64_t blk_block_pad(int32_t nrows, int32_t ncols, int32_t n, int32_t right_kernel)
+{
+        int64_t N = right_kernel ? ncols : nrows, Mc = right_kernel ? nrows : ncols;
+        int64_t a = ((N + n - 1) / n) * n, b = ((Mc + n - 1) / n) * n;
+        return (a > b ? a : b) * n;
+}
+
+int blk_destroy(blk_ctx *c)
+{
+        if (!c) return 0;
+        cudaSetDevice(c->device);
+        if (c->stream) cudaStreamSynchronize(c->stream);
+        destroy_graph(c);
+        if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+        free_operator(&c->S1);
+        free_operator(&c->S2);
+        cudaFree(c->v); cudaFree(c->tmp); cudaFree(c->Av); cudaFree(c->p);
+        cudaFree(c->partials); cudaFree(c->mats); cudaFree(c->sums); cudaFree(c->state);
+        if (c->h_state) cudaFreeHost(c->h_state);
+        if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+        delete c;
+        return 0;
+}
+
+int blk_create(blk_ctx **out, const blk_params *prm)
+{
+        *out = nullptr;
+        if (!prm || prm->abi_version != BLK_ABI_VERSION) return fail("blk_params.abi_version mismatch");
+        if (prm->n < 1 || prm->n > BLK_MAX_N) return fail("blocking factor n must be in [1,64]");
+        if (prm->nrows < 1 || prm->ncols < 1 || prm->nnz < 0) return fail("bad matrix dimensions");
+        if (prm->nnz > 0 && (!prm->Mi || !prm->Mj || !prm->Mx)) return fail("null COO arrays");
+        int world = prm->world > 0 ? prm->world : 1;
+        if (prm->rank < 0 || prm->rank >= world) return fail("rank out of range");
+        if (world > 1 && !prm->nccl_id) return fail("world > 1 needs blk_params.nccl_id");
+        ModP m;
+        if (!modp_make(&m, prm->prime)) return fail("prime must satisfy 2 <= p < 2^31");
+        int ndev = 0;
+        cudaError_t e0 = cudaGetDeviceCount(&ndev);
+        if (e0 != cudaSuccess || ndev == 0)
+                return fail(std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e0));
+        if (prm->device < 0 || prm->device >= ndev) return fail("device ordinal out of range");
+        CU(cudaSetDevice(prm->device));
+
+        blk_ctx *c = new blk_ctx();
+        c->geo = make_geometry(prm->n);
+        c->m = m;
+        c->device = prm->device; c->rank = prm->rank; c->world = world; c->right = prm->right_kernel ? 1 : 0;
+        c->nrows = prm->nrows; c->ncols = prm->ncols;
+        c->N = c->right ? prm->ncols : prm->nrows;
+        c->Mc = c->right ? prm->nrows : prm->ncols;
+        c->use_graph = prm->use_graph;
+        const int np = c->geo.np;
+#define CUX(call)                                                                                  \
+        do {                                                                                       \
+                cudaError_t e_ = (call);                                                           \
+                if (e_ != cudaSuccess) {                                                           \
+                        fail(std::string(#call) + ": " + cudaGetErrorString(e_));                  \
+                        blk_destroy(c);                                                            \
+                        return 1;                                                                  \
+                }                                                                                  \
+        } while (0)
+        if (prm->stream) c->stream = (cudaStream_t)prm->stream;
+        else { CUX(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+
+        dense_prepare(c->geo, c->m);
+
+        // ---- COO on the device
+        const int64_t nnz = prm->nnz;
+        int32_t *di = nullptr, *dj = nullptr;
+        u32 *dx = nullptr;
+        bool own_coo = false;
+        if (prm->coo_on_device || nnz == 0) {
+                di = (int32_t *)prm->Mi; dj = (int32_t *)prm->Mj; dx = (u32 *)prm->Mx;
+        } else {
+                own_coo = true;
+                CUX(cudaMalloc(&di, sizeof(int32_t) * (size_t)nnz));
+                CUX(cudaMalloc(&dj, sizeof(int32_t) * (size_t)nnz));
+                CUX(cudaMalloc(&dx, sizeof(u32) * (size_t)nnz));
+                CUX(cudaMemcpyAsync(di, prm->Mi, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
+                CUX(cudaMemcpyAsync(dj, prm->Mj, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
+                CUX(cudaMemcpyAsync(dx, prm->Mx, sizeof(u32) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
+        }
+        auto free_coo = [&]() { if (own_coo) { cudaFree(di); cudaFree(dj); cudaFree(dx); } };
+
+        // Lanczos-dimension index array and the other one
+        const int32_t *idxN = c->right ? dj : di;     // indexes rows of v/Av/p
+        const int32_t *idxM = c->right ? di : dj;     // indexes rows of tmp
+
+        // ---- row partitions
+        c->n_off.assign(world + 1, 0); c->m_off.assign(world + 1, 0);
+        c->n_off[world] = c->N; c->m_off[world] = c->Mc;
+        if (world > 1) {
+                for (int pass = 0; pass < 2; pass++) {
+                        int64_t dim = pass ? c->Mc : c->N;
+                        u32 *dc = nullptr;
+                        CUX(cudaMalloc(&dc, sizeof(u32) * (size_t)dim));
+                        CUX(cudaMemsetAsync(dc, 0, sizeof(u32) * (size_t)dim, c->stream));
+                        if (nnz) k_count_rows<<<nb(nnz), 256, 0, c->stream>>>(nnz, pass ? idxM : idxN, dim, dc);
+                        std::vector<u32> hc((size_t)dim);
+                        CUX(cudaMemcpyAsync(hc.data(), dc, sizeof(u32) * (size_t)dim, cudaMemcpyDeviceToHost, c->stream));
+                        CUX(cudaStreamSynchronize(c->stream));
+                        cudaFree(dc);
+                        (pass ? c->m_off : c->n_off) = partition_rows(hc, world);
+                }
+        }
+
+        // ---- the two operators.  S1: rows = my block of the Mc dimension, columns = N dimension;
+        //      S2: rows = my block of the N dimension, columns = Mc dimension.
+        for (int which = 0; which < 2; which++) {
+                SpOp *op = which ? &c->S2 : &c->S1;
+                const int32_t *rk = which ? idxN : idxM, *ck = which ? idxM : idxN;
+                int64_t lo = which ? c->n0() : c->m0(), hi = which ? c->n1() : c->m1();
+                int64_t cols = which ? c->Mc : c->N;
+                std::string err;
+                if (world == 1) {
+                        err = build_operator(op, c->geo, prm->chunk_len, hi - lo, cols, lo, nnz, rk, ck, dx, m.p, c->stream);
+                } else {
+                        int32_t *sr = nullptr, *sc = nullptr; u32 *sx = nullptr;
+                        unsigned long long *cnt = nullptr, hcnt = 0;
+                        // upper bound of the selection is not known: count first
+                        CUX(cudaMalloc(&cnt, sizeof(unsigned long long)));
+                        u32 *dc = nullptr;
+                        int64_t dim = which ? c->N : c->Mc;
+                        CUX(cudaMalloc(&dc, sizeof(u32) * (size_t)dim));
+                        CUX(cudaMemsetAsync(dc, 0, sizeof(u32) * (size_t)dim, c->stream));
+                        if (nnz) k_count_rows<<<nb(nnz), 256, 0, c->stream>>>(nnz, rk, dim, dc);
+                        std::vector<u32> hc((size_t)(hi - lo));
+                        if (hi > lo)
+                                CUX(cudaMemcpyAsync(hc.data(), dc + lo, sizeof(u32) * (size_t)(hi - lo), cudaMemcpyDeviceToHost, c->stream));
+                        CUX(cudaStreamSynchronize(c->stream));
+                        cudaFree(dc);
+                        int64_t sel = 0;
+                        for (u32 q : hc) sel += q;
+                        int64_t cap = sel > 0 ? sel : 1;
+                        CUX(cudaMalloc(&sr, sizeof(int32_t) * (size_t)cap));
+                        CUX(cudaMalloc(&sc, sizeof(int32_t) * (size_t)cap));
+                        CUX(cudaMalloc(&sx, sizeof(u32) * (size_t)cap));
+                        CUX(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
+                        if (nnz) k_select_range<<<nb(nnz), 256, 0, c->stream>>>(nnz, rk, ck, dx, lo, hi, sr, sc, sx, cnt);
+                        CUX(cudaMemcpyAsync(&hcnt, cnt, sizeof(hcnt), cudaMemcpyDeviceToHost, c->stream));
+                        CUX(cudaStreamSynchronize(c->stream));
+                        cudaFree(cnt);
+                        if ((int64_t)hcnt != sel) err = "shard selection count mismatch";
+                        else err = build_operator(op, c->geo, prm->chunk_len, hi - lo, cols, lo, sel, sr, sc, sx, m.p, c->stream);
+                        cudaFree(sr); cudaFree(sc); cudaFree(sx);
+                }
+                if (!err.empty()) { free_coo(); fail(err); blk_destroy(c); return 1; }
+        }
+        CUX(cudaStreamSynchronize(c->stream));
+        free_coo();
+
+        // ---- vector blocks and the small working set
+        int64_t ln = c->n1() - c->n0();
+        size_t bv = sizeof(u32) * (size_t)c->N * np, bt = sizeof(u32) * (size_t)c->Mc * np;
+        size_t bl = sizeof(u32) * (size_t)(ln > 0 ? ln : 1) * np;
+        CUX(cudaMalloc(&c->v, bv)); CUX(cudaMalloc(&c->tmp, bt));
+        CUX(cudaMalloc(&c->Av, bl)); CUX(cudaMalloc(&c->p, bl));
+        CUX(cudaMemsetAsync(c->v, 0, bv, c->stream)); CUX(cudaMemsetAsync(c->tmp, 0, bt, c->stream));
+        CUX(cudaMemsetAsync(c->Av, 0, bl, c->stream)); CUX(cudaMemsetAsync(c->p, 0, bl, c->stream));
+        c->block_bytes = bv + bt + 2 * bl;
+        c->dots_blocks = dots_num_blocks(ln, np);
+        CUX(cudaMalloc(&c->partials, sizeof(u32) * (size_t)c->dots_blocks * 2 * np * np));
+        CUX(cudaMalloc(&c->mats, sizeof(u32) * (size_t)MAT_COUNT * np * np));
+        CUX(cudaMalloc(&c->sums, sizeof(u64) * (size_t)2 * np * np));
+        CUX(cudaMalloc(&c->state, sizeof(DevSmall)));
+        CUX(cudaMallocHost(&c->h_state, sizeof(DevSmall)));
+        CUX(cudaMemsetAsync(c->mats, 0, sizeof(u32) * (size_t)MAT_COUNT * np * np, c->stream));
+        memset(c->h_state, 0, sizeof(DevSmall));
+        c->h_state->halt = 1;
+        if (push_state(c)) { blk_destroy(c); return 1; }
+        CUX(cudaStreamSynchronize(c->stream));
+
+        if (world > 1) {
+                std::string why;
+                if (!nccl_load(&why)) { fail(why); blk_destroy(c); return 1; }
+                ncclUniqueId id;
+                memcpy(&id, prm->nccl_id, sizeof(id));
+                ncclResult_t r = g_nccl.CommInitRank(&c->comm, world, id, c->rank);
+                if (r != ncclSuccess) {
+                        fail(std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
+                        blk_destroy(c);
+                        return 1;
+                }
+        }
+#undef CUX
+        *out = c;
+        return 0;
+}
+
+int blk_set_state(blk_ctx *c, const uint32_t *v, const uint32_t *p, int32_t n_iterations)
+{
+        if (!c || !v) return fail("blk_set_state: null argument");
+        CU(cudaSetDevice(c->device));
+        const int np = c->geo.np, n = c->geo.n;
+        if (upload_rows(c, c->v, v, c->N)) return 1;
+        int64_t ln = c->n1() - c->n0();
+        if (p) {
+                if (upload_rows(c, c->p, p + (size_t)c->n0() * n, ln)) return 1;
+        } else {
+                CU(cudaMemsetAsync(c->p, 0, sizeof(u32) * (size_t)(ln > 0 ? ln : 1) * np, c->stream));
+        }
+        CU(cudaMemsetAsync(c->tmp, 0, sizeof(u32) * (size_t)c->Mc * np, c->stream));
+        CU(cudaMemsetAsync(c->Av, 0, sizeof(u32) * (size_t)(ln > 0 ? ln : 1) * np, c->stream));
+        c->iters = n_iterations; c->stopped = 0;
+        c->tmp_is_spmv = false; c->any_ortho = n_iterations > 0;
+        memset(c->h_state, 0, sizeof(DevSmall));
+        c->h_state->iters = n_iterations;
+        c->h_state->halt = 1;
+        if (push_state(c)) return 1;
+        CU(cudaStreamSynchronize(c->stream));
+        return 0;
+}
+
+int blk_iterate(blk_ctx *c, int32_t max_iters, int32_t *iters_total, int32_t *stopped)
+{
+        if (!c) return fail("blk_iterate: null context");
+        CU(cudaSetDevice(c->device));
+        if (max_iters > 0 && !c->stopped) {
+                c->h_state->iters = c->iters;
+                c->h_state->limit = c->iters + max_iters;
+                c->h_state->stopped = 0; c->h_state->halt = 0; c->h_state->do_ortho = 0;
+                if (push_state(c)) return 1;
+                bool graph = c->use_graph == 1 || (c->use_graph < 0 && c->world == 1 && max_iters >= 4);
+                if (c->profiling || c->world > 1) graph = false;
+                EventTimer tm;
+                int done = 0;
+                if (graph && !c->graph) {
+                        // first iteration runs un-captured so that every kernel is loaded before capture
+                        if (enqueue_iteration(c, nullptr)) return 1;
+                        done = 1;
+                        if (build_graph(c)) return 1;
+                }
+                const int check_every = graph ? 16 * blk_ctx::GRAPH_ITERS : 64;
+                while (done < max_iters) {
+                        int batch = std::min(check_every, max_iters - done);
+                        if (graph) {
+                                int ng = (batch + blk_ctx::GRAPH_ITERS - 1) / blk_ctx::GRAPH_ITERS;
+                                for (int i = 0; i < ng; i++) CU(cudaGraphLaunch(c->graph, c->stream));
+                                c->launches += (int64_t)ng * blk_ctx::GRAPH_ITERS * kernels_per_iteration(c);
+                        } else {
+                                for (int i = 0; i < batch; i++)
+                                        if (enqueue_iteration(c, c->profiling ? &tm : nullptr)) return 1;
+                        }
+                        done += batch;
+                        if (pull_state(c)) return 1;
+                        if (c->profiling) tm.resolve(c);
+                        if (c->h_state->halt) break;
+                }
+                int before = c->iters;
+                c->iters = c->h_state->iters;
+                c->stopped = c->h_state->stopped;
+                if (c->stopped) c->tmp_is_spmv = true;
+                else if (c->iters > before) c->tmp_is_spmv = false;
+                if (c->iters > before) c->any_ortho = true;
+        }
+        if (iters_total) *iters_total = c->iters;
+        if (stopped) *stopped = c->stopped;
+        return 0;
+}
+
+int blk_get_state(blk_ctx *c, uint32_t *v, uint32_t *tmp, uint32_t *Av, uint32_t *p)
+{
+        if (!c) return fail("blk_get_state: null context");
+        CU(cudaSetDevice(c->device));
+        const int n = c->geo.n, np = c->geo.np;
+        const int64_t pad = blk_block_pad(c->nrows, c->ncols, n, c->right);
+        const int64_t N = c->N, Mc = c->Mc;
+        // v is complete on every rank only right after an all-gather; refresh it
+        if (c->world > 1 && allgather_rows(c, c->v, c->n_off)) return 1;
+        std::vector<u32> hv;
+        const u32 *vsrc = nullptr;
+        if (v || tmp) {
+                hv.resize((size_t)N * n);
+                if (download_rows(c, hv.data(), c->v, N)) return 1;
+                vsrc = hv.data();
+        }
+        if (v) {
+                memset(v, 0, sizeof(u32) * (size_t)pad);
+                memcpy(v, vsrc, sizeof(u32) * (size_t)N * n);
+        }
+        if (tmp) {
+                // see DESIGN.md "tmp": the reference's tmp holds the next v in rows [0,N) after
+                // orthogonalize + copy (:652-656) and S1*v in rows [0,Mc) after the first product (:635)
+                memset(tmp, 0, sizeof(u32) * (size_t)pad);
+                std::vector<u32> ht((size_t)Mc * n);
+                if (download_rows(c, ht.data(), c->tmp, Mc)) return 1;
+                if (c->tmp_is_spmv) {
+                        if (c->any_ortho && N > Mc)
+                                memcpy(tmp + (size_t)Mc * n, vsrc + (size_t)Mc * n, sizeof(u32) * (size_t)(N - Mc) * n);
+                        memcpy(tmp, ht.data(), sizeof(u32) * (size_t)Mc * n);
+                } else {
+                        if (Mc > N)
+                                memcpy(tmp + (size_t)N * n, ht.data() + (size_t)N * n, sizeof(u32) * (size_t)(Mc - N) * n);
+                        if (c->any_ortho) memcpy(tmp, vsrc, sizeof(u32) * (size_t)N * n);
+                        else memcpy(tmp, ht.data(), sizeof(u32) * (size_t)std::min(N, Mc) * n);
+                }
+        }
+        for (int which = 0; which < 2; which++) {
+                uint32_t *dst = which ? p : Av;
+                if (!dst) continue;
+                memset(dst, 0, sizeof(u32) * (size_t)pad);
+                u32 *src = which ? c->p : c->Av;
+                if (c->world == 1) {
+                        if (download_rows(c, dst, src, N)) return 1;
+                } else {
+                        u32 *full = nullptr;
+                        CU(cudaMalloc(&full, sizeof(u32) * (size_t)N * np));
+                        int64_t ln = c->n1() - c->n0();
+                        CU(cudaMemcpyAsync(full + (size_t)c->n0() * np, src, sizeof(u32) * (size_t)ln * np,
+                                           cudaMemcpyDeviceToDevice, c->stream));
+                        if (allgather_rows(c, full, c->n_off)) { cudaFree(full); return 1; }
+                        int rc = download_rows(c, dst, full, N);
+                        cudaFree(full);
+                        if (rc) return 1;
+                }
+        }
+        return 0;
+}
+
+int blk_get_small(blk_ctx *c, uint32_t *vtAv, uint32_t *vtAAv, uint32_t *winv, uint32_t *d, int32_t *npiv)
+{
+        if (!c) return fail("blk_get_small: null context");
+        CU(cudaSetDevice(c->device));
+        const int n = c->geo.n, np = c->geo.np;
+        std::vector<u32> h((size_t)MAT_COUNT * np * np);
+        CU(cudaMemcpyAsync(h.data(), c->mats, sizeof(u32) * h.size(), cudaMemcpyDeviceToHost, c->stream));
+        if (pull_state(c)) return 1;
+        auto take = [&](uint32_t *dst, int which) {
+                if (!dst) return;
+                for (int i = 0; i < n; i++)
+                        for (int j = 0; j < n; j++) dst[i * n + j] = h[(size_t)which * np * np + i * np + j];
+        };
+        take(vtAv, MAT_VTAV); take(vtAAv, MAT_VTAAV); take(winv, MAT_WINV);
+        if (d) for (int j = 0; j < n; j++) d[j] = h[(size_t)MAT_D * np * np + j];
+        if (npiv) *npiv = c->h_state->npiv;
+        return 0;
+}
+
+// ---- per-function entry points -----------------------------------------------------------
+static SpOp *op_for(blk_ctx *c, int transpose, bool *is_s1)
+{
+        // S1 is M^T for --left and M for --right (sequential/lanczos_modp.c:635)
+        bool s1 = (transpose != 0) == (c->right == 0);
+        *is_s1 = s1;
+        return s1 ? &c->S1 : &c->S2;
+}
+
+int blk_spmv(blk_ctx *c, uint32_t *y, const uint32_t *x, int32_t transpose)
+{
+        if (!c || !y || !x) return fail("blk_spmv: null argument");
+        CU(cudaSetDevice(c->device));
+        const int np = c->geo.np;
+        bool s1;
+        SpOp *op = op_for(c, transpose, &s1);
+        const std::vector<int64_t> &off = s1 ? c->m_off : c->n_off;
+        int64_t out_rows = s1 ? c->Mc : c->N, in_rows = s1 ? c->N : c->Mc;
+        u32 *dx = nullptr, *dy = nullptr;
+        CU(cudaMalloc(&dx, sizeof(u32) * (size_t)in_rows * np));
+        CU(cudaMalloc(&dy, sizeof(u32) * (size_t)out_rows * np));
+        int rc = upload_rows(c, dx, x, in_rows);
+        if (!rc) {
+                // poison the output: every row must be written by the kernels
+                cudaMemsetAsync(dy, 0xff, sizeof(u32) * (size_t)out_rows * np, c->stream);
+                int k = launch_spmv(*op, c->geo, c->m, dx, dy + (size_t)off[c->rank] * np, nullptr, c->stream);
+                c->launches += k;
+                if (c->world > 1) rc = allgather_rows(c, dy, off);
+        }
+        if (!rc) rc = download_rows(c, y, dy, out_rows);
+        cudaError_t e = cudaGetLastError();
+        cudaFree(dx); cudaFree(dy);
+        if (!rc && e != cudaSuccess) return fail(std::string("blk_spmv: ") + cudaGetErrorString(e));
+        return rc;
+}
+
+int blk_block_dot_products(blk_ctx *c, uint32_t *vtAv, uint32_t *vtAAv, int64_t N, const uint32_t *Av,
+                           const uint32_t *v)
+{
+        if (!c || !vtAv || !vtAAv || !Av || !v || N < 0) return fail("blk_block_dot_products: bad argument");
+        CU(cudaSetDevice(c->device));
+        const int np = c->geo.np, n = c->geo.n;
+        u32 *dv = nullptr, *da = nullptr, *part = nullptr, *mats = nullptr;
+        int64_t rows = N > 0 ? N : 1;
+        int nblocks = dots_num_blocks(N, np);
+        CU(cudaMalloc(&dv, sizeof(u32) * (size_t)rows * np));
+        CU(cudaMalloc(&da, sizeof(u32) * (size_t)rows * np));
+        CU(cudaMalloc(&part, sizeof(u32) * (size_t)nblocks * 2 * np * np));
+        CU(cudaMalloc(&mats, sizeof(u32) * (size_t)MAT_COUNT * np * np));
+        int rc = upload_rows(c, dv, v, N) || upload_rows(c, da, Av, N);
+        if (!rc) {
+                c->launches += launch_dots(c->geo, c->m, N, dv, da, part, nblocks, nullptr, c->stream);
+                c->launches += launch_small(c->geo, c->m, part, nblocks, nullptr, mats, c->state, 1, c->stream);
+                std::vector<u32> h((size_t)2 * np * np);
+                cudaMemcpyAsync(h.data(), mats, sizeof(u32) * h.size(), cudaMemcpyDeviceToHost, c->stream);
+                cudaError_t e = cudaStreamSynchronize(c->stream);
+                if (e != cudaSuccess) rc = fail(std::string("blk_block_dot_products: ") + cudaGetErrorString(e));
+                else
+                        for (int i = 0; i < n; i++)
+                                for (int j = 0; j < n; j++) {
+                                        vtAv[i * n + j] = h[(size_t)MAT_VTAV * np * np + i * np + j];
+                                        vtAAv[i * n + j] = h[(size_t)MAT_VTAAV * np * np + i * np + j];
+                                }
+        }
+        cudaFree(dv); cudaFree(da); cudaFree(part); cudaFree(mats);
+        return rc;
+}
+
+static void put_small(std::vector<u32> &h, int which, const uint32_t *src, int n, int np)
+{
+        for (int i = 0; i < n; i++)
+                for (int j = 0; j < n; j++) h[(size_t)which * np * np + i * np + j] = src[i * n + j];
+}
+
+int blk_semi_inverse(blk_ctx *c, const uint32_t *M_, uint32_t *winv, uint32_t *d, int32_t *npiv)
+{
+        if (!c || !M_ || !winv || !d) return fail("blk_semi_inverse: null argument");
+        CU(cudaSetDevice(c->device));
+        const int np = c->geo.np, n = c->geo.n;
+        std::vector<u32> h((size_t)MAT_COUNT * np * np, 0);
+        put_small(h, MAT_VTAV, M_, n, np);
+        u32 *mats = nullptr;
+        DevSmall *st = nullptr;
+        CU(cudaMalloc(&mats, sizeof(u32) * h.size()));
+        CU(cudaMalloc(&st, sizeof(DevSmall)));
+        CU(cudaMemsetAsync(st, 0, sizeof(DevSmall), c->stream));
+        CU(cudaMemcpyAsync(mats, h.data(), sizeof(u32) * h.size(), cudaMemcpyHostToDevice, c->stream));
+        c->launches += launch_small(c->geo, c->m, nullptr, 0, nullptr, mats, st, 2, c->stream);
+        DevSmall hs;
+        CU(cudaMemcpyAsync(h.data(), mats, sizeof(u32) * h.size(), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(&hs, st, sizeof(DevSmall), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(mats); cudaFree(st);
+        for (int i = 0; i < n; i++)
+                for (int j = 0; j < n; j++) winv[i * n + j] = h[(size_t)MAT_WINV * np * np + i * np + j];
+        for (int j = 0; j < n; j++) d[j] = h[(size_t)MAT_D * np * np + j];
+        if (npiv) *npiv = hs.npiv;
+        return 0;
+}
+
+int blk_orthogonalize(blk_ctx *c, const uint32_t *v, uint32_t *tmp, uint32_t *p, const uint32_t *d,
+                      const uint32_t *vtAv, const uint32_t *vtAAv, const uint32_t *winv, int64_t N,
+                      const uint32_t *Av)
+{
+        if (!c || !v || !tmp || !p || !d || !vtAv || !vtAAv || !winv || !Av || N < 0)
+                return fail("blk_orthogonalize: bad argument");
+        CU(cudaSetDevice(c->device));
+        const int np = c->geo.np, n = c->geo.n;
+        std::vector<u32> h((size_t)MAT_COUNT * np * np, 0);
+        put_small(h, MAT_VTAV, vtAv, n, np);
+        put_small(h, MAT_VTAAV, vtAAv, n, np);
+        put_small(h, MAT_WINV, winv, n, np);
+        for (int j = 0; j < n; j++) h[(size_t)MAT_D * np * np + j] = d[j];
+        int64_t rows = N > 0 ? N : 1;
+        u32 *mats = nullptr, *dv = nullptr, *da = nullptr, *dp = nullptr, *dvo = nullptr;
+        CU(cudaMalloc(&mats, sizeof(u32) * h.size()));
+        CU(cudaMalloc(&dv, sizeof(u32) * (size_t)rows * np));
+        CU(cudaMalloc(&dvo, sizeof(u32) * (size_t)rows * np));
+        CU(cudaMalloc(&da, sizeof(u32) * (size_t)rows * np));
+        CU(cudaMalloc(&dp, sizeof(u32) * (size_t)rows * np));
+        CU(cudaMemcpyAsync(mats, h.data(), sizeof(u32) * h.size(), cudaMemcpyHostToDevice, c->stream));
+        int rc = upload_rows(c, dv, v, N) || upload_rows(c, da, Av, N) || upload_rows(c, dp, p, N);
+        if (!rc && N > 0) {
+                c->launches += launch_small(c->geo, c->m, nullptr, 0, nullptr, mats, c->state, 3, c->stream);
+                c->launches += launch_ortho(c->geo, c->m, N, dv, da, dp, dvo, dp, mats, c->state, 1, c->stream);
+                rc = download_rows(c, tmp, dvo, N) || download_rows(c, p, dp, N);
+                cudaError_t e = cudaGetLastError();
+                if (!rc && e != cudaSuccess) rc = fail(std::string("blk_orthogonalize: ") + cudaGetErrorString(e));
+        }
+        cudaFree(mats); cudaFree(dv); cudaFree(dvo); cudaFree(da); cudaFree(dp);
+        return rc;
+}
+
+// ---- measurement ---------------------------------------------------------------------------
+int blk_set_profiling(blk_ctx *c, int32_t on)
+{
+        if (!c) return fail("null context");
+        c->profiling = on != 0;
+        for (int i = 0; i < BLK_PH_COUNT; i++) { c->ph_ms[i] = 0; c->ph_launch[i] = 0; }
+        return 0;
+}
+
+int blk_get_phase_times(blk_ctx *c, double ms[BLK_PH_COUNT], int64_t launches[BLK_PH_COUNT])
+{
+        if (!c) return fail("null context");
+        for (int i = 0; i < BLK_PH_COUNT; i++) {
+                if (ms) ms[i] = c->ph_ms[i];
+                if (launches) launches[i] = c->ph_launch[i];
+        }
+        return 0;
+}
+
+int blk_time_spmv(blk_ctx *c, int32_t transpose, int32_t reps, double *ms_avg)
+{
+        if (!c || reps < 1 || !ms_avg) return fail("blk_time_spmv: bad argument");
+        CU(cudaSetDevice(c->device));
+        const int np = c->geo.np;
+        bool s1;
+        SpOp *op = op_for(c, transpose, &s1);
+        const u32 *x = s1 ? c->v : c->tmp;
+        u32 *y = s1 ? c->tmp + (size_t)c->m0() * np : c->Av;
+        cudaEvent_t a, b;
+        CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+        c->launches += launch_spmv(*op, c->geo, c->m, x, y, nullptr, c->stream);    // warm-up
+        CU(cudaEventRecord(a, c->stream));
+        for (int i = 0; i < reps; i++) c->launches += launch_spmv(*op, c->geo, c->m, x, y, nullptr, c->stream);
+        CU(cudaEventRecord(b, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, a, b));
+        cudaEventDestroy(a); cudaEventDestroy(b);
+        *ms_avg = (double)ms / reps;
+        c->tmp_is_spmv = false;
+        return 0;
+}
+
+int64_t blk_kernel_launches(blk_ctx *c) { return c ? c->launches : 0; }
+
+int blk_get_info(blk_ctx *c, blk_info *info)
+{
+        if (!c || !info) return fail("blk_get_info: null argument");
+        memset(info, 0, sizeof(*info));
+        info->N = c->N; info->Mc = c->Mc;
+        info->local_N0 = c->n0(); info->local_N1 = c->n1();
+        info->local_M0 = c->m0(); info->local_M1 = c->m1();
+        const SpOp *ops[2] = {&c->S1, &c->S2};
+        for (int i = 0; i < 2; i++) {
+                info->nnz_local[i] = ops[i]->nnz;
+                info->stored_local[i] = ops[i]->stored;
+                info->tiles[i] = ops[i]->ntiles;
+                info->chunk_len[i] = ops[i]->Q;
+        }
+        info->n = c->geo.n; info->n_pad = c->geo.np; info->groups_per_warp = c->geo.G;
+        info->device_bytes = (int64_t)(c->S1.bytes + c->S2.bytes + c->block_bytes);
+        return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,532 @@
+// dense.cu -- the tall-skinny GF(p) phases of one block-Lanczos iteration:
+//
+//   k_dots    vtAv = v^T Av, vtAAv = Av^T Av                (block_dot_products, sequential/lanczos_modp.c:443-453,
+//                                                           built there from matmul_CpAtB :305-315)
+//   k_small   sum of partials, semi_inverse, c / vtAvd      (semi_inverse :342-438; the n x n part of orthogonalize :460-475)
+//   k_ortho   next v and p, row by row                      (orthogonalize :478-491 built from matmul_CpAB :292-302,
+//                                                           and the v <- tmp copy :655-656, here a no-op: v is updated in place)
+//
+// The reference does a 64-bit `%` per multiply-add; these kernels accumulate in u64 with the
+// lazy fold of modp.cuh and reduce once per output.  Blocks are stored with leading dimension
+// n_pad (power of two >= n, extra columns are zero and stay zero through every phase).
+#include "blk_internal.cuh"
+
+namespace {
+
+constexpr int DOTS_TB = 256;
+
+template <int V> struct VecD;
+template <> struct VecD<1> { typedef unsigned int T; };
+template <> struct VecD<2> { typedef uint2 T; };
+template <> struct VecD<4> { typedef uint4 T; };
+
+template <int V> __device__ __forceinline__ void ldv(u32 (&o)[V], const u32 *p)
+{
+        typename VecD<V>::T t = *reinterpret_cast<const typename VecD<V>::T *>(p);
+        const u32 *w = reinterpret_cast<const u32 *>(&t);
+#pragma unroll
+        for (int k = 0; k < V; k++) o[k] = w[k];
+}
+template <int V> __device__ __forceinline__ void stv(u32 *p, const u32 (&o)[V])
+{
+        typename VecD<V>::T t;
+        u32 *w = reinterpret_cast<u32 *>(&t);
+#pragma unroll
+        for (int k = 0; k < V; k++) w[k] = o[k];
+        *reinterpret_cast<typename VecD<V>::T *>(p) = t;
+}
+
+// ------------------------------------------------------------------------------------------
+// dots: a team of T = (NP/TI)^2 threads owns the NP x NP outputs (TI x TI register tile per
+// thread, for both matrices); teams stride over the rows.  partials[block][2][NP*NP], reduced.
+// ------------------------------------------------------------------------------------------
+template <int NP, int FOLD>
+__global__ void __launch_bounds__(DOTS_TB)
+k_dots(int64_t rows, const u32 *__restrict__ v, const u32 *__restrict__ Av, u32 *__restrict__ partials,
+       ModP m, const DevSmall *__restrict__ state)
+{
+        constexpr int TI = NP < 4 ? NP : 4;
+        constexpr int PER = NP / TI;          // tiles per dimension
+        constexpr int T = PER * PER;          // threads per team
+        constexpr int TEAMS = DOTS_TB / T;
+        constexpr int FE = FOLD ? FOLD : 64;  // rows between folds
+        if (state && state->halt) return;
+
+        const int tid = threadIdx.x;
+        const int team = tid / T, tt = tid % T;
+        const int i0 = (tt / PER) * TI, j0 = (tt % PER) * TI;
+        u64 a1[TI][TI], a2[TI][TI];
+#pragma unroll
+        for (int a = 0; a < TI; a++)
+#pragma unroll
+                for (int b = 0; b < TI; b++) { a1[a][b] = 0; a2[a][b] = 0; }
+
+        const int64_t stride = (int64_t)gridDim.x * TEAMS;
+        int since = 0;
+        for (int64_t r = (int64_t)blockIdx.x * TEAMS + team; r < rows; r += stride) {
+                u32 vi[TI], ai[TI], aj[TI];
+                ldv<TI>(vi, v + r * NP + i0);
+                ldv<TI>(ai, Av + r * NP + i0);
+                ldv<TI>(aj, Av + r * NP + j0);
+#pragma unroll
+                for (int a = 0; a < TI; a++)
+#pragma unroll
+                        for (int b = 0; b < TI; b++) {
+                                mp_mac(a1[a][b], vi[a], aj[b]);
+                                mp_mac(a2[a][b], ai[a], aj[b]);
+                        }
+                if (++since == FE) {
+                        since = 0;
+#pragma unroll
+                        for (int a = 0; a < TI; a++)
+#pragma unroll
+                                for (int b = 0; b < TI; b++) { mp_fold(a1[a][b], m); mp_fold(a2[a][b], m); }
+                }
+        }
+
+        u32 *out = partials + (size_t)blockIdx.x * 2 * NP * NP;
+        if (TEAMS == 1) {
+#pragma unroll
+                for (int a = 0; a < TI; a++)
+#pragma unroll
+                        for (int b = 0; b < TI; b++) {
+                                out[(i0 + a) * NP + j0 + b] = mp_reduce(a1[a][b], m);
+                                out[NP * NP + (i0 + a) * NP + j0 + b] = mp_reduce(a2[a][b], m);
+                        }
+        } else {
+                __shared__ unsigned long long acc[TEAMS == 1 ? 1 : 2 * NP * NP];
+                for (int e = tid; e < 2 * NP * NP; e += DOTS_TB) acc[e] = 0;
+                __syncthreads();
+#pragma unroll
+                for (int a = 0; a < TI; a++)
+#pragma unroll
+                        for (int b = 0; b < TI; b++) {
+                                atomicAdd(&acc[(i0 + a) * NP + j0 + b], (unsigned long long)mp_reduce(a1[a][b], m));
+                                atomicAdd(&acc[NP * NP + (i0 + a) * NP + j0 + b], (unsigned long long)mp_reduce(a2[a][b], m));
+                        }
+                __syncthreads();
+                for (int e = tid; e < 2 * NP * NP; e += DOTS_TB) out[e] = mp_reduce(acc[e], m);
+        }
+}
+
+__global__ void k_partials_to_sums(int np2x2, const u32 *__restrict__ partials, int nblocks,
+                                   u64 *__restrict__ sums, const DevSmall *__restrict__ state)
+{
+        if (state && state->halt) return;
+        int e = blockIdx.x * blockDim.x + threadIdx.x;
+        if (e >= np2x2) return;
+        u64 s = 0;
+        for (int b = 0; b < nblocks; b++) s += partials[(size_t)b * np2x2 + e];
+        sums[e] = s;
+}
+
+// ------------------------------------------------------------------------------------------
+// small: one block.  Working matrices use the true n as leading dimension in shared memory.
+// ------------------------------------------------------------------------------------------
+constexpr int SMALL_TB = 256;
+
+// Gauss-Jordan sweep shared by both phases of semi_inverse (sequential/lanczos_modp.c:351-382,
+// :393-436): first non-zero at or below the diagonal is the pivot, the pivot row is scaled to 1,
+// swapped into place, and column j is cleared in every other row.  W (may be null) receives the
+// same row operations.  Returns the number of pivots; d[j] = 1 on pivot columns.
+__device__ int gj_sweep(u32 *M, u32 *W, u32 *d, u32 *mult, int *ctl, int n, const ModP &m)
+{
+        const int tid = threadIdx.x;
+        int found = 0;
+        for (int j = tid; j < n; j += SMALL_TB) d[j] = 0;
+        __syncthreads();
+        for (int j = 0; j < n; j++) {
+                if (tid < 32) {
+                        // rows tid and tid+32
+                        bool h0 = (tid >= j && tid < n) ? M[tid * n + j] != 0 : false;
+                        bool h1 = (tid + 32 >= j && tid + 32 < n) ? M[(tid + 32) * n + j] != 0 : false;
+                        unsigned b0 = __ballot_sync(0xffffffffu, h0), b1 = __ballot_sync(0xffffffffu, h1);
+                        if (tid == 0) {
+                                int piv = b0 ? __ffs(b0) - 1 : (b1 ? 32 + __ffs(b1) - 1 : -1);
+                                ctl[0] = piv;
+                                if (piv >= 0) ctl[1] = (int)mp_inv(M[piv * n + j], m);
+                        }
+                }
+                __syncthreads();
+                const int piv = ctl[0];
+                if (piv < 0) { __syncthreads(); continue; }
+                const u32 inv = (u32)ctl[1];
+                found++;
+                for (int k = tid; k < n; k += SMALL_TB) {
+                        u32 a = mp_mul(M[piv * n + k], inv, m);
+                        M[piv * n + k] = M[j * n + k];
+                        M[j * n + k] = a;
+                        if (W) {
+                                u32 b = mp_mul(W[piv * n + k], inv, m);
+                                W[piv * n + k] = W[j * n + k];
+                                W[j * n + k] = b;
+                        }
+                }
+                if (tid == 0) d[j] = 1;
+                __syncthreads();
+                for (int i = tid; i < n; i += SMALL_TB) mult[i] = (i == j) ? 0u : mp_neg(M[i * n + j], m);
+                __syncthreads();
+                for (int e = tid; e < n * n; e += SMALL_TB) {
+                        int i = e / n, k = e - i * n;
+                        if (i == j) continue;
+                        u32 f = mult[i];
+                        if (f == 0) continue;
+                        M[e] = mp_reduce((u64)M[e] + (u64)f * M[j * n + k], m);
+                        if (W) W[e] = mp_reduce((u64)W[e] + (u64)f * W[j * n + k], m);
+                }
+                __syncthreads();
+        }
+        return found;
+}
+
+// mode 0: full step; 1: reduce dots only; 2: semi_inverse of mats[VTAV]; 3: coefficients only
+__global__ void __launch_bounds__(SMALL_TB)
+k_small(int n, int np, const u32 *__restrict__ partials, int nblocks, const u64 *__restrict__ sums,
+        u32 *__restrict__ mats, DevSmall *__restrict__ state, int mode, ModP m)
+{
+        extern __shared__ u32 sm[];
+        const int tid = threadIdx.x;
+        const int nn = n * n, npp = np * np;
+        u32 *A = sm;               // vtAv   (n x n)
+        u32 *B = A + nn;           // vtAAv
+        u32 *M = B + nn;           // elimination work matrix
+        u32 *W = M + nn;           // winv
+        u32 *d = W + nn;           // n
+        u32 *d1 = d + n;           // n (phase-1 pivots)
+        u32 *mult = d1 + n;        // n
+        int *ctl = (int *)(mult + n);
+
+        if (mode == 0 && state->halt) {
+                if (tid == 0) state->do_ortho = 0;
+                return;
+        }
+
+        // ---- gather the dot products
+        if (mode <= 1) {
+                for (int e = tid; e < 2 * nn; e += SMALL_TB) {
+                        int which = e / nn, r = e - which * nn;
+                        int i = r / n, j = r - i * n;
+                        int src = which * npp + i * np + j;
+                        u64 s = 0;
+                        if (partials) {
+                                for (int b = 0; b < nblocks; b++) s += partials[(size_t)b * 2 * npp + src];
+                        } else {
+                                s = sums[src];
+                        }
+                        (which ? B : A)[r] = mp_reduce(s, m);
+                }
+                __syncthreads();
+                for (int e = tid; e < 2 * npp; e += SMALL_TB) {
+                        int which = e / npp, r = e - which * npp;
+                        int i = r / np, j = r - i * np;
+                        u32 val = (i < n && j < n) ? (which ? B : A)[i * n + j] : 0u;
+                        mats[(which ? MAT_VTAAV : MAT_VTAV) * npp + r] = val;
+                }
+                if (mode == 1) return;
+        } else {
+                for (int e = tid; e < nn; e += SMALL_TB) {
+                        int i = e / n, j = e - i * n;
+                        A[e] = mats[MAT_VTAV * npp + i * np + j];
+                        B[e] = mats[MAT_VTAAV * npp + i * np + j];
+                }
+        }
+        __syncthreads();
+
+        int npiv = 0;
+        if (mode == 0 || mode == 2) {
+                // ---- semi_inverse, phase 1: which columns carry a pivot
+                for (int e = tid; e < nn; e += SMALL_TB) M[e] = A[e];
+                __syncthreads();
+                gj_sweep(M, nullptr, d1, mult, ctl, n, m);
+                // ---- phase 2 on the d x d restriction, carrying winv along
+                for (int e = tid; e < nn; e += SMALL_TB) {
+                        int i = e / n, j = e - i * n;
+                        bool keep = d1[i] && d1[j];
+                        M[e] = keep ? A[e] : 0u;
+                        W[e] = (i == j && d1[i]) ? 1u : 0u;
+                }
+                __syncthreads();
+                npiv = gj_sweep(M, W, d, mult, ctl, n, m);
+                for (int e = tid; e < npp; e += SMALL_TB) {
+                        int i = e / np, j = e - i * np;
+                        mats[MAT_WINV * npp + e] = (i < n && j < n) ? W[i * n + j] : 0u;
+                }
+                for (int j = tid; j < np; j += SMALL_TB) mats[MAT_D * npp + j] = j < n ? d[j] : 0u;
+                if (tid == 0) state->npiv = npiv;
+                if (mode == 2) return;
+        } else {
+                for (int e = tid; e < nn; e += SMALL_TB) {
+                        int i = e / n, j = e - i * n;
+                        W[e] = mats[MAT_WINV * npp + i * np + j];
+                }
+                for (int j = tid; j < n; j += SMALL_TB) d[j] = mats[MAT_D * npp + j];
+                __syncthreads();
+                npiv = 1;
+        }
+
+        // ---- coefficients of orthogonalize (sequential/lanczos_modp.c:460-475)
+        //   c     = -(winv * spliced), spliced[:,j] = d[j] ? vtAAv[:,j] : vtAv[:,j]
+        //   vtAvd = d[j] ? -vtAv[:,j] : 0
+        // (the reference stores p - x, which may equal p; canonical here, same value mod p)
+        for (int e = tid; e < npp; e += SMALL_TB) {
+                int i = e / np, j = e - i * np;
+                u32 cval = 0, dval = 0;
+                if (i < n && j < n) {
+                        const u32 *S = d[j] ? B : A;
+                        u64 s = 0;
+                        for (int k = 0; k < n; k++) {
+                                s += (u64)W[i * n + k] * S[k * n + j];
+                                mp_fold(s, m);
+                        }
+                        cval = mp_neg(mp_reduce(s, m), m);
+                        dval = d[j] ? mp_neg(A[i * n + j], m) : 0u;
+                }
+                mats[MAT_C * npp + e] = cval;
+                mats[MAT_VTAVD * npp + e] = dval;
+        }
+
+        if (mode == 0 && tid == 0) {
+                if (npiv == 0) {
+                        state->stopped = 1; state->halt = 1; state->do_ortho = 0;
+                } else {
+                        int it = state->iters + 1;
+                        state->iters = it;
+                        state->do_ortho = 1;
+                        if (state->limit > 0 && it >= state->limit) state->halt = 1;
+                }
+        }
+}
+
+// ------------------------------------------------------------------------------------------
+// ortho: each row independently,
+//   v'[r,:] = (d ? Av[r,:] : v[r,:]) + v[r,:] c + p[r,:] vtAvd
+//   p'[r,:] = (d ? 0 : p[r,:])       + v[r,:] winv
+// NP/JT threads per row, JT output columns each; the three n x n matrices sit in shared memory
+// and are read with warp-broadcast LDS.128.
+// ------------------------------------------------------------------------------------------
+constexpr int ORTHO_TB = 128;
+
+template <int NP, int JT, int FOLD>
+__global__ void __launch_bounds__(ORTHO_TB)
+k_ortho(int64_t rows, const u32 *v, const u32 *__restrict__ Av, const u32 *p, u32 *v_out, u32 *p_out,
+        const u32 *__restrict__ mats, ModP m, const DevSmall *__restrict__ state, int force)
+{
+        constexpr int TPR = NP / JT;
+        constexpr int KV = NP < 4 ? NP : 4;
+        constexpr int JV = JT < 4 ? JT : 4;
+        constexpr int FV = FOLD ? FOLD / 2 : 32;     // k-steps between folds of accV (2 products per k)
+        constexpr int FP = FOLD ? FOLD : 64;         // ... of accP (1 product per k)
+        extern __shared__ u32 sm[];
+        u32 *C = sm, *D = C + NP * NP, *Wm = D + NP * NP, *dm = Wm + NP * NP;
+        if (!force && !state->do_ortho) return;
+        for (int e = threadIdx.x; e < NP * NP; e += ORTHO_TB) {
+                C[e] = mats[MAT_C * NP * NP + e];
+                D[e] = mats[MAT_VTAVD * NP * NP + e];
+                Wm[e] = mats[MAT_WINV * NP * NP + e];
+        }
+        for (int e = threadIdx.x; e < NP; e += ORTHO_TB) dm[e] = mats[MAT_D * NP * NP + e];
+        __syncthreads();
+
+        const int64_t gid = (int64_t)blockIdx.x * ORTHO_TB + threadIdx.x;
+        const int64_t r = gid / TPR;
+        const int j0 = (int)(gid % TPR) * JT;
+        const bool active = r < rows;
+        u64 accV[JT], accP[JT];
+#pragma unroll
+        for (int j = 0; j < JT; j++) { accV[j] = 0; accP[j] = 0; }
+        u32 nv[JT], npw[JT];
+        if (active) {
+                const u32 *vr = v + r * NP, *pr = p + r * NP;
+#pragma unroll
+                for (int k0 = 0; k0 < NP; k0 += KV) {
+                        u32 vk[KV], pk[KV];
+                        ldv<KV>(vk, vr + k0);
+                        ldv<KV>(pk, pr + k0);
+#pragma unroll
+                        for (int kk = 0; kk < KV; kk++) {
+                                const int k = k0 + kk;
+#pragma unroll
+                                for (int jj = 0; jj < JT; jj += JV) {
+                                        u32 cc[JV], dd[JV], ww[JV];
+                                        ldv<JV>(cc, C + k * NP + j0 + jj);
+                                        ldv<JV>(dd, D + k * NP + j0 + jj);
+                                        ldv<JV>(ww, Wm + k * NP + j0 + jj);
+#pragma unroll
+                                        for (int j = 0; j < JV; j++) {
+                                                mp_mac(accV[jj + j], vk[kk], cc[j]);
+                                                mp_mac(accV[jj + j], pk[kk], dd[j]);
+                                                mp_mac(accP[jj + j], vk[kk], ww[j]);
+                                        }
+                                }
+                                if ((k + 1) % FV == 0) {
+#pragma unroll
+                                        for (int j = 0; j < JT; j++) mp_fold(accV[j], m);
+                                }
+                                if ((k + 1) % FP == 0) {
+#pragma unroll
+                                        for (int j = 0; j < JT; j++) mp_fold(accP[j], m);
+                                }
+                        }
+                }
+#pragma unroll
+                for (int jj = 0; jj < JT; jj += JV) {
+                        u32 av[JV], vb[JV], pb[JV];
+                        ldv<JV>(av, Av + r * NP + j0 + jj);
+                        ldv<JV>(vb, vr + j0 + jj);
+                        ldv<JV>(pb, pr + j0 + jj);
+#pragma unroll
+                        for (int j = 0; j < JV; j++) {
+                                bool dj = dm[j0 + jj + j] != 0;
+                                nv[jj + j] = mp_add(mp_reduce(accV[jj + j], m), dj ? av[j] : vb[j], m);
+                                npw[jj + j] = mp_add(mp_reduce(accP[jj + j], m), dj ? 0u : pb[j], m);
+                        }
+                }
+        }
+        if (TPR > 1) __syncwarp();      // in place: every lane of the row has read v, p before anyone writes
+        if (active) {
+#pragma unroll
+                for (int jj = 0; jj < JT; jj += JV) {
+                        u32 a[JV], b[JV];
+#pragma unroll
+                        for (int j = 0; j < JV; j++) { a[j] = nv[jj + j]; b[j] = npw[jj + j]; }
+                        stv<JV>(v_out + r * NP + j0 + jj, a);
+                        stv<JV>(p_out + r * NP + j0 + jj, b);
+                }
+        }
+}
+
+__global__ void k_pad_rows(const u32 *__restrict__ src, u32 *__restrict__ dst, int64_t rows, int n, int np)
+{
+        int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (e >= rows * np) return;
+        int64_t r = e / np;
+        int j = (int)(e - r * np);
+        dst[e] = j < n ? src[r * n + j] : 0u;
+}
+__global__ void k_unpad_rows(const u32 *__restrict__ src, u32 *__restrict__ dst, int64_t rows, int n, int np)
+{
+        int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (e >= rows * n) return;
+        int64_t r = e / n;
+        int j = (int)(e - r * n);
+        dst[e] = src[r * np + j];
+}
+
+template <int NP>
+int dots_fold(const ModP &m, int64_t rows, const u32 *v, const u32 *Av, u32 *partials, int nblocks,
+              const DevSmall *state, cudaStream_t st)
+{
+        switch (m.fold_every) {
+        case 0: k_dots<NP, 0><<<nblocks, DOTS_TB, 0, st>>>(rows, v, Av, partials, m, state); break;
+        case 8: k_dots<NP, 8><<<nblocks, DOTS_TB, 0, st>>>(rows, v, Av, partials, m, state); break;
+        default: k_dots<NP, 2><<<nblocks, DOTS_TB, 0, st>>>(rows, v, Av, partials, m, state); break;
+        }
+        return 1;
+}
+
+template <int NP, int JT, int FOLD>
+void ortho_go(int64_t rows, u32 *v, const u32 *Av, u32 *p, u32 *v_out, u32 *p_out, const u32 *mats,
+              const ModP &m, const DevSmall *state, int force, cudaStream_t st)
+{
+        size_t smem = sizeof(u32) * (3 * NP * NP + NP);
+        if (rows < 0) {         // prepare only: opt in to > 48 KB of dynamic shared memory (per device)
+                if (smem > 48 * 1024)
+                        cudaFuncSetAttribute(k_ortho<NP, JT, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                return;
+        }
+        int64_t threads = rows * (NP / JT);
+        unsigned blocks = (unsigned)((threads + ORTHO_TB - 1) / ORTHO_TB);
+        k_ortho<NP, JT, FOLD><<<blocks, ORTHO_TB, smem, st>>>(rows, v, Av, p, v_out, p_out, mats, m, state, force);
+}
+
+template <int NP, int JT>
+int ortho_fold(int64_t rows, u32 *v, const u32 *Av, u32 *p, u32 *v_out, u32 *p_out, const u32 *mats,
+               const ModP &m, const DevSmall *state, int force, cudaStream_t st)
+{
+        switch (m.fold_every) {
+        case 0: ortho_go<NP, JT, 0>(rows, v, Av, p, v_out, p_out, mats, m, state, force, st); break;
+        case 8: ortho_go<NP, JT, 8>(rows, v, Av, p, v_out, p_out, mats, m, state, force, st); break;
+        default: ortho_go<NP, JT, 2>(rows, v, Av, p, v_out, p_out, mats, m, state, force, st); break;
+        }
+        return 1;
+}
+
+}  // namespace
+
+int dots_num_blocks(int64_t rows, int np)
+{
+        int ti = np < 4 ? np : 4;
+        int team = (np / ti) * (np / ti);
+        int teams = DOTS_TB / team;
+        int64_t want = (rows + (int64_t)teams * 16 - 1) / ((int64_t)teams * 16);   // >= 16 rows per team
+        if (want < 1) want = 1;
+        if (want > 148 * 4) want = 148 * 4;
+        return (int)want;
+}
+
+int launch_dots(const Geometry &geo, const ModP &m, int64_t rows, const u32 *v, const u32 *Av,
+                u32 *partials, int nblocks, const DevSmall *state, cudaStream_t st)
+{
+        switch (geo.np) {
+        case 1: return dots_fold<1>(m, rows, v, Av, partials, nblocks, state, st);
+        case 2: return dots_fold<2>(m, rows, v, Av, partials, nblocks, state, st);
+        case 4: return dots_fold<4>(m, rows, v, Av, partials, nblocks, state, st);
+        case 8: return dots_fold<8>(m, rows, v, Av, partials, nblocks, state, st);
+        case 16: return dots_fold<16>(m, rows, v, Av, partials, nblocks, state, st);
+        case 32: return dots_fold<32>(m, rows, v, Av, partials, nblocks, state, st);
+        case 64: return dots_fold<64>(m, rows, v, Av, partials, nblocks, state, st);
+        }
+        return -1;
+}
+
+int launch_partials_to_sums(const Geometry &geo, const ModP &, const u32 *partials, int nblocks,
+                            u64 *sums, const DevSmall *state, cudaStream_t st)
+{
+        int cnt = 2 * geo.np * geo.np;
+        k_partials_to_sums<<<(cnt + 255) / 256, 256, 0, st>>>(cnt, partials, nblocks, sums, state);
+        return 1;
+}
+
+int launch_small(const Geometry &geo, const ModP &m, const u32 *partials, int nblocks, const u64 *sums,
+                 u32 *mats, DevSmall *state, int mode, cudaStream_t st)
+{
+        size_t smem = sizeof(u32) * (4 * (size_t)geo.n * geo.n + 3 * geo.n + 8);
+        k_small<<<1, SMALL_TB, smem, st>>>(geo.n, geo.np, partials, nblocks, sums, mats, state, mode, m);
+        return 1;
+}
+
+int launch_ortho(const Geometry &geo, const ModP &m, int64_t rows, u32 *v, const u32 *Av, u32 *p,
+                 u32 *v_out, u32 *p_out, const u32 *mats, const DevSmall *state, int force, cudaStream_t st)
+{
+        switch (geo.np) {
+        case 1: return ortho_fold<1, 1>(rows, v, Av, p, v_out, p_out, mats, m, state, force, st);
+        case 2: return ortho_fold<2, 2>(rows, v, Av, p, v_out, p_out, mats, m, state, force, st);
+        case 4: return ortho_fold<4, 4>(rows, v, Av, p, v_out, p_out, mats, m, state, force, st);
+        case 8: return ortho_fold<8, 8>(rows, v, Av, p, v_out, p_out, mats, m, state, force, st);
+        case 16: return ortho_fold<16, 16>(rows, v, Av, p, v_out, p_out, mats, m, state, force, st);
+        case 32: return ortho_fold<32, 16>(rows, v, Av, p, v_out, p_out, mats, m, state, force, st);
+        case 64: return ortho_fold<64, 16>(rows, v, Av, p, v_out, p_out, mats, m, state, force, st);
+        }
+        return -1;
+}
+
+void dense_prepare(const Geometry &geo, const ModP &m)
+{
+        cudaFuncSetAttribute(k_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        launch_ortho(geo, m, -1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr);
+}
+
+int launch_pad_rows(const u32 *src, u32 *dst, int64_t rows, int n, int np, cudaStream_t st)
+{
+        int64_t tot = rows * np;
+        if (tot == 0) return 0;
+        k_pad_rows<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(src, dst, rows, n, np);
+        return 1;
+}
+int launch_unpad_rows(const u32 *src, u32 *dst, int64_t rows, int n, int np, cudaStream_t st)
+{
+        int64_t tot = rows * n;
+        if (tot == 0) return 0;
+        k_unpad_rows<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(src, dst, rows, n, np);
+        return 1;
+}

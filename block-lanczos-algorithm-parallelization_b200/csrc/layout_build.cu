@@ -1,0 +1,259 @@
+// layout_build.cu -- COO triplets (struct sparsematrix_t, sequential/lanczos_modp.c:55-62)
+// -> GPU-resident interleaved chunk stream (see blk_internal.cuh).  Runs once per operator at
+// blk_create time, entirely on the device: key build + radix sort (CUB) + scans + scatter.
+// The reference never builds a row-ordered layout (it scatters from COO on every product,
+// sequential/lanczos_modp.c:277-286); sorting is legal because results are canonical residues
+// and therefore independent of summation order.
+#include <cub/cub.cuh>
+#include "blk_internal.cuh"
+
+#define CK(call)                                                                                   \
+        do {                                                                                       \
+                cudaError_t e_ = (call);                                                           \
+                if (e_ != cudaSuccess)                                                             \
+                        return std::string(#call) + ": " + cudaGetErrorString(e_);                 \
+        } while (0)
+
+namespace {
+
+constexpr int TB = 256;
+inline unsigned nblk(int64_t n) { return (unsigned)((n + TB - 1) / TB); }
+
+__global__ void k_make_keys(int64_t nnz, const int32_t *__restrict__ row, const int32_t *__restrict__ col,
+                            const u32 *__restrict__ val, int64_t row_lo, int64_t rows, int64_t cols, u32 p,
+                            u64 *__restrict__ keys, u32 *__restrict__ vals, u32 *__restrict__ cnt,
+                            int *__restrict__ bad)
+{
+        int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (s >= nnz) return;
+        int64_t r = (int64_t)row[s] - row_lo;
+        int64_t c = col[s];
+        if (r < 0 || r >= rows || c < 0 || c >= cols) {
+                *bad = 1;
+                r = 0; c = 0;
+        }
+        keys[s] = ((u64)r << 32) | (u64)c;
+        vals[s] = val[s] % p;                       // Mx[u] = x % prime, sequential/lanczos_modp.c:243
+        atomicAdd(&cnt[r], 1u);
+}
+
+__global__ void k_row_lengths(int64_t rows, const u32 *__restrict__ cnt, u64 *__restrict__ len,
+                              u32 *__restrict__ empty)
+{
+        int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (r > rows) return;
+        if (r == rows) { len[r] = 0; return; }
+        u32 c = cnt[r];
+        len[r] = c ? c : 1;
+        empty[r] = c ? 0u : 1u;
+}
+
+__device__ __forceinline__ int64_t interleave(int64_t pos, int G, int Q)
+{
+        int64_t tile = (int64_t)G * Q;
+        int64_t t = pos / tile;
+        int o = (int)(pos - t * tile);
+        int g = o / Q, i = o - g * Q;
+        return t * tile + (int64_t)i * G + g;
+}
+
+__global__ void k_scatter(int64_t nnz, const u64 *__restrict__ keys, const u32 *__restrict__ vals,
+                          const u32 *__restrict__ empties_before, uint2 *__restrict__ ent, int G, int Q)
+{
+        int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (s >= nnz) return;
+        u64 k = keys[s];
+        u32 r = (u32)(k >> 32);
+        bool last = (s == nnz - 1) || ((u32)(keys[s + 1] >> 32) != r);
+        int64_t pos = s + (int64_t)empties_before[r];
+        ent[interleave(pos, G, Q)] = make_uint2((u32)k | (last ? 0x80000000u : 0u), vals[s]);
+}
+
+__global__ void k_dummies(int64_t rows, const u32 *__restrict__ cnt, const u64 *__restrict__ rowptr,
+                          uint2 *__restrict__ ent, int G, int Q)
+{
+        int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (r >= rows || cnt[r]) return;
+        ent[interleave((int64_t)rowptr[r], G, Q)] = make_uint2(0x80000000u, 0u);
+}
+
+// largest r in [0, rows] with rowptr[r] <= pos   (rowptr has rows+1 entries, non-decreasing)
+__device__ __forceinline__ int64_t row_of(const u64 *__restrict__ rowptr, int64_t rows, u64 pos)
+{
+        int64_t lo = 0, hi = rows;          // invariant rowptr[lo] <= pos
+        while (lo < hi) {
+                int64_t mid = (lo + hi + 1) >> 1;
+                if (rowptr[mid] <= pos) lo = mid; else hi = mid - 1;
+        }
+        return lo;
+}
+
+__global__ void k_chunk_rows(int64_t nchunks, int Q, int64_t stored, int64_t rows,
+                             const u64 *__restrict__ rowptr, u32 *__restrict__ chunk_row)
+{
+        int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (k >= nchunks) return;
+        u64 pos = (u64)k * (u64)Q;
+        if ((int64_t)pos >= stored) { chunk_row[k] = (u32)rows; return; }   // pure padding
+        int64_t r = row_of(rowptr, rows, pos);
+        // rows has no zero-length rows (dummies), so rowptr is strictly increasing below `rows`
+        u32 open = rowptr[r] < pos ? 0x80000000u : 0u;
+        chunk_row[k] = (u32)r | open;
+}
+
+__global__ void k_tile_tails(int64_t ntiles, int64_t tile, int64_t stored, int64_t rows,
+                             const u64 *__restrict__ rowptr, u32 *__restrict__ tail_row,
+                             u32 *__restrict__ span)
+{
+        int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (t >= ntiles) return;
+        u32 tr = 0xffffffffu, sp = 0;
+        int64_t end = (t + 1) * tile;
+        if (end < stored) {
+                int64_t r = row_of(rowptr, rows, (u64)(end - 1));
+                int64_t rs = (int64_t)rowptr[r], re = (int64_t)rowptr[r + 1];
+                if (re > end && rs >= t * tile) {           // row starts in this tile and runs past it
+                        tr = (u32)r;
+                        sp = (u32)((re - 1) / tile - t);
+                }
+        }
+        tail_row[t] = tr;
+        span[t] = sp;
+}
+
+}  // namespace
+
+void free_operator(SpOp *op)
+{
+        cudaFree(op->ent); cudaFree(op->chunk_row); cudaFree(op->tail_row);
+        cudaFree(op->span); cudaFree(op->whead);
+        *op = SpOp();
+}
+
+static int pick_chunk_len(int64_t stored, int G)
+{
+        // aim for >= 8 warps on each of the 148 SMs; cap the chunk so that u64 accumulators never
+        // chain more than 64 products (modp.cuh)
+        int Q = 32;
+        while (Q > 8 && stored / ((int64_t)G * Q) < 148 * 8) Q >>= 1;
+        return Q;
+}
+
+std::string build_operator(SpOp *op, const Geometry &geo, int chunk_len, int64_t rows, int64_t cols,
+                           int64_t row_lo, int64_t nnz, const int32_t *d_row, const int32_t *d_col,
+                           const u32 *d_val, u32 prime, cudaStream_t st)
+{
+        *op = SpOp();
+        op->rows = rows; op->cols = cols; op->nnz = nnz; op->G = geo.G;
+        if (rows >= (1ll << 31) || cols >= (1ll << 31)) return "matrix dimension >= 2^31";
+        if (chunk_len != 0 && (chunk_len < 8 || chunk_len > 64 || (chunk_len & (chunk_len - 1))))
+                return "chunk_len must be a power of two in [8,64]";
+
+        u32 *cnt = nullptr, *empty = nullptr, *vals[2] = {nullptr, nullptr};
+        u64 *keys[2] = {nullptr, nullptr}, *rowptr = nullptr;
+        void *tmp = nullptr;
+        int *bad = nullptr;
+        std::string err;
+        auto cleanup = [&]() {
+                cudaFree(cnt); cudaFree(empty); cudaFree(vals[0]); cudaFree(vals[1]);
+                cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(rowptr); cudaFree(tmp); cudaFree(bad);
+        };
+#define CKC(call)                                                                                  \
+        do {                                                                                       \
+                cudaError_t e_ = (call);                                                           \
+                if (e_ != cudaSuccess) {                                                           \
+                        err = std::string(#call) + ": " + cudaGetErrorString(e_);                  \
+                        cleanup(); free_operator(op);                                              \
+                        return err;                                                                \
+                }                                                                                  \
+        } while (0)
+
+        int64_t nn = nnz > 0 ? nnz : 1;
+        CKC(cudaMalloc(&cnt, sizeof(u32) * (size_t)(rows + 1)));
+        CKC(cudaMalloc(&empty, sizeof(u32) * (size_t)(rows + 1)));
+        CKC(cudaMalloc(&rowptr, sizeof(u64) * (size_t)(rows + 1)));
+        CKC(cudaMalloc(&bad, sizeof(int)));
+        CKC(cudaMemsetAsync(cnt, 0, sizeof(u32) * (size_t)(rows + 1), st));
+        CKC(cudaMemsetAsync(empty, 0, sizeof(u32) * (size_t)(rows + 1), st));
+        CKC(cudaMemsetAsync(bad, 0, sizeof(int), st));
+        for (int b = 0; b < 2; b++) {
+                CKC(cudaMalloc(&keys[b], sizeof(u64) * (size_t)nn));
+                CKC(cudaMalloc(&vals[b], sizeof(u32) * (size_t)nn));
+        }
+        if (nnz > 0) {
+                k_make_keys<<<nblk(nnz), TB, 0, st>>>(nnz, d_row, d_col, d_val, row_lo, rows, cols, prime,
+                                                      keys[0], vals[0], cnt, bad);
+                CKC(cudaGetLastError());
+        }
+        int h_bad = 0;
+        CKC(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CKC(cudaStreamSynchronize(st));
+        if (h_bad) {
+                cleanup(); free_operator(op);
+                return "matrix entry with row/column index out of range";
+        }
+
+        // sort by (row, col)
+        cub::DoubleBuffer<u64> dk(keys[0], keys[1]);
+        cub::DoubleBuffer<u32> dv(vals[0], vals[1]);
+        if (nnz > 1) {
+                int rbits = 1;
+                while ((1ll << rbits) < rows) rbits++;
+                size_t tb = 0;
+                CKC(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, nnz, 0, 32 + rbits, st));
+                CKC(cudaMalloc(&tmp, tb ? tb : 16));
+                CKC(cub::DeviceRadixSort::SortPairs(tmp, tb, dk, dv, nnz, 0, 32 + rbits, st));
+                CKC(cudaStreamSynchronize(st));
+                cudaFree(tmp); tmp = nullptr;
+        }
+
+        // stored row pointers (every row >= 1 entry) and the number of empty rows before each row
+        k_row_lengths<<<nblk(rows + 1), TB, 0, st>>>(rows, cnt, rowptr, empty);
+        CKC(cudaGetLastError());
+        {
+                size_t tb1 = 0, tb2 = 0;
+                CKC(cub::DeviceScan::ExclusiveSum(nullptr, tb1, rowptr, rowptr, rows + 1, st));
+                CKC(cub::DeviceScan::ExclusiveSum(nullptr, tb2, empty, empty, rows + 1, st));
+                size_t tb = tb1 > tb2 ? tb1 : tb2;
+                CKC(cudaMalloc(&tmp, tb ? tb : 16));
+                CKC(cub::DeviceScan::ExclusiveSum(tmp, tb1, rowptr, rowptr, rows + 1, st));
+                CKC(cub::DeviceScan::ExclusiveSum(tmp, tb2, empty, empty, rows + 1, st));
+        }
+        u64 h_stored = 0;
+        CKC(cudaMemcpyAsync(&h_stored, rowptr + rows, sizeof(u64), cudaMemcpyDeviceToHost, st));
+        CKC(cudaStreamSynchronize(st));
+        cudaFree(tmp); tmp = nullptr;
+        op->stored = (int64_t)h_stored;
+
+        op->Q = chunk_len ? chunk_len : pick_chunk_len(op->stored, geo.G);
+        int64_t tile = (int64_t)op->G * op->Q;
+        op->ntiles = (op->stored + tile - 1) / tile;
+        if (op->ntiles < 1) op->ntiles = 1;
+        int64_t nchunks = op->ntiles * op->G;
+        if (op->ntiles * tile >= (1ll << 40)) { cleanup(); free_operator(op); return "operator too large"; }
+
+        size_t ent_b = sizeof(uint2) * (size_t)(op->ntiles * tile);
+        CKC(cudaMalloc(&op->ent, ent_b));
+        CKC(cudaMalloc(&op->chunk_row, sizeof(u32) * (size_t)nchunks));
+        CKC(cudaMalloc(&op->tail_row, sizeof(u32) * (size_t)op->ntiles));
+        CKC(cudaMalloc(&op->span, sizeof(u32) * (size_t)op->ntiles));
+        CKC(cudaMalloc(&op->whead, sizeof(u32) * (size_t)op->ntiles * geo.np));
+        op->bytes = ent_b + sizeof(u32) * (size_t)(nchunks + 2 * op->ntiles + op->ntiles * geo.np);
+        CKC(cudaMemsetAsync(op->ent, 0, ent_b, st));
+        CKC(cudaMemsetAsync(op->whead, 0, sizeof(u32) * (size_t)op->ntiles * geo.np, st));
+        if (nnz > 0) {
+                k_scatter<<<nblk(nnz), TB, 0, st>>>(nnz, dk.Current(), dv.Current(), empty, op->ent, op->G, op->Q);
+                CKC(cudaGetLastError());
+        }
+        k_dummies<<<nblk(rows), TB, 0, st>>>(rows, cnt, rowptr, op->ent, op->G, op->Q);
+        CKC(cudaGetLastError());
+        k_chunk_rows<<<nblk(nchunks), TB, 0, st>>>(nchunks, op->Q, op->stored, rows, rowptr, op->chunk_row);
+        CKC(cudaGetLastError());
+        k_tile_tails<<<nblk(op->ntiles), TB, 0, st>>>(op->ntiles, tile, op->stored, rows, rowptr,
+                                                      op->tail_row, op->span);
+        CKC(cudaGetLastError());
+        CKC(cudaStreamSynchronize(st));
+        cleanup();
+        return "";
+#undef CKC
+}

@@ -1,0 +1,218 @@
+// spmv.cu -- y(R x n) <- S x(C x n) over GF(p) on the interleaved chunk stream.
+//
+// Replaces sparse_matrix_vector_product (sequential/lanczos_modp.c:266-287): the reference
+// scatters from unsorted COO with a read-modify-write of y and a 64-bit `%` per multiply-add.
+// Here every output row is produced by a gather over its own entries (no atomics), products
+// are accumulated lazily in u64 (modp.cuh) and reduced once per row segment.
+//
+// Mapping: one warp per tile of G chunks; lane-group g (L lanes, V columns each) walks chunk g.
+// Per step the warp issues one coalesced 8-byte-per-group load of {col|LAST, val} and one
+// gather of the x row (V*4 bytes per lane, n_pad*4 contiguous bytes per group).  U steps are
+// software-unrolled so that U independent gathers are in flight per lane.
+// HBM bytes per entry: 8 (matrix) + 4*n_pad (x row, when x does not fit L2) -- see DESIGN.md.
+#include "blk_internal.cuh"
+
+namespace {
+
+constexpr int WARPS = 8;     // warps (tiles) per thread block
+constexpr int U = 8;         // unroll: gathers in flight per lane
+
+template <int V> struct Vec;
+template <> struct Vec<1> { typedef unsigned int T; };
+template <> struct Vec<2> { typedef uint2 T; };
+template <> struct Vec<4> { typedef uint4 T; };
+
+template <int V> __device__ __forceinline__ void load_vec(u32 (&o)[V], const u32 *p)
+{
+        typename Vec<V>::T t = __ldg(reinterpret_cast<const typename Vec<V>::T *>(p));
+        const u32 *w = reinterpret_cast<const u32 *>(&t);
+#pragma unroll
+        for (int k = 0; k < V; k++) o[k] = w[k];
+}
+template <int V> __device__ __forceinline__ void load_vec_rw(u32 (&o)[V], const u32 *p)
+{
+        typename Vec<V>::T t = *reinterpret_cast<const typename Vec<V>::T *>(p);
+        const u32 *w = reinterpret_cast<const u32 *>(&t);
+#pragma unroll
+        for (int k = 0; k < V; k++) o[k] = w[k];
+}
+template <int V> __device__ __forceinline__ void store_vec(u32 *p, const u32 (&o)[V])
+{
+        typename Vec<V>::T t;
+        u32 *w = reinterpret_cast<u32 *>(&t);
+#pragma unroll
+        for (int k = 0; k < V; k++) w[k] = o[k];
+        *reinterpret_cast<typename Vec<V>::T *>(p) = t;
+}
+
+template <int L, int V, int FOLD>
+__global__ void __launch_bounds__(WARPS * 32)
+k_spmv(const uint2 *__restrict__ ent, const u32 *__restrict__ chunk_row, u32 *__restrict__ whead,
+       int64_t ntiles, int Q, u32 rows, const u32 *__restrict__ x, u32 *__restrict__ y, ModP m,
+       const DevSmall *__restrict__ state)
+{
+        constexpr int G = 32 / L;
+        constexpr int NP = L * V;
+        if (state && state->halt) return;
+        const int lane = threadIdx.x & 31;
+        const int64_t t = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+        if (t >= ntiles) return;
+        const int g = lane / L, sub = lane % L;
+
+        const u32 cr = __ldg(chunk_row + t * G + g);
+        u32 row = cr & 0x7fffffffu;
+        bool head_open = (cr >> 31) != 0;
+        const uint2 *e = ent + t * G * Q + g;
+        const u32 *xs = x + sub * V;
+        u32 *ys = y + sub * V;
+
+        u64 acc[V];
+        u32 headv[V];
+#pragma unroll
+        for (int k = 0; k < V; k++) { acc[k] = 0; headv[k] = 0; }
+        int head_type = 0;              // 0 none, 1 row ended inside the chunk, 2 whole chunk inside one row
+        bool pending = false;
+
+        for (int i0 = 0; i0 < Q; i0 += U) {
+                uint2 ee[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) ee[u] = __ldg(e + (size_t)(i0 + u) * G);
+                u32 xv[U][V];
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                        load_vec<V>(xv[u], xs + (size_t)(ee[u].x & 0x7fffffffu) * NP);
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+#pragma unroll
+                        for (int k = 0; k < V; k++) mp_mac(acc[k], ee[u].y, xv[u][k]);
+                        if (FOLD != 0 && (u % (FOLD ? FOLD : 1)) == (FOLD ? FOLD : 1) - 1) {
+#pragma unroll
+                                for (int k = 0; k < V; k++) mp_fold(acc[k], m);
+                        }
+                        pending = true;
+                        if (ee[u].x & 0x80000000u) {            // last entry of its row
+                                u32 r[V];
+#pragma unroll
+                                for (int k = 0; k < V; k++) { r[k] = mp_reduce(acc[k], m); acc[k] = 0; }
+                                if (head_open) {
+#pragma unroll
+                                        for (int k = 0; k < V; k++) headv[k] = r[k];
+                                        head_type = 1;
+                                        head_open = false;
+                                } else {
+                                        store_vec<V>(ys + (size_t)row * NP, r);
+                                }
+                                row++;
+                                pending = false;
+                        }
+                }
+        }
+
+        u32 tailv[V];
+#pragma unroll
+        for (int k = 0; k < V; k++) tailv[k] = 0;
+        bool has_tail = false;
+        if (pending) {
+                if (head_open) {
+#pragma unroll
+                        for (int k = 0; k < V; k++) headv[k] = mp_reduce(acc[k], m);
+                        head_type = 2;
+                } else if (row < rows) {            // row == rows: trailing padding only
+#pragma unroll
+                        for (int k = 0; k < V; k++) tailv[k] = mp_reduce(acc[k], m);
+                        has_tail = true;
+                }
+        }
+
+        // stitch rows that cross chunk borders inside the warp: suffix scan over the groups.
+        // S = sum of chunk heads from this chunk up to (and including) the chunk where the
+        // row ends; closed = that chunk lies inside the warp.
+        int closed = head_type != 2;
+#pragma unroll
+        for (int d = 1; d < G; d <<= 1) {
+                u32 sp[V];
+#pragma unroll
+                for (int k = 0; k < V; k++) sp[k] = __shfl_down_sync(0xffffffffu, headv[k], d * L);
+                int cp = __shfl_down_sync(0xffffffffu, closed, d * L);
+                if (!closed && g + d < G) {
+#pragma unroll
+                        for (int k = 0; k < V; k++) headv[k] = mp_add(headv[k], sp[k], m);
+                        closed = cp;
+                }
+        }
+        u32 nx[V];
+#pragma unroll
+        for (int k = 0; k < V; k++) nx[k] = __shfl_down_sync(0xffffffffu, headv[k], L);
+        if (has_tail) {
+                // complete if the row ends inside this warp, else a partial finished by k_spmv_fix
+                u32 o[V];
+#pragma unroll
+                for (int k = 0; k < V; k++) o[k] = (g < G - 1) ? mp_add(tailv[k], nx[k], m) : tailv[k];
+                store_vec<V>(ys + (size_t)row * NP, o);
+        }
+        if (g == 0 && head_type != 0) store_vec<V>(whead + t * NP + sub * V, headv);
+}
+
+// rows that cross tile borders: y[row] (partial left by the tile where the row starts) plus the
+// heads of the `span` following tiles.
+template <int L, int V>
+__global__ void __launch_bounds__(256)
+k_spmv_fix(const u32 *__restrict__ tail_row, const u32 *__restrict__ span, const u32 *__restrict__ whead,
+           int64_t ntiles, u32 *__restrict__ y, ModP m, const DevSmall *__restrict__ state)
+{
+        constexpr int NP = L * V;
+        if (state && state->halt) return;
+        int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / L;
+        int sub = threadIdx.x % L;
+        if (gid >= ntiles) return;
+        u32 sp = __ldg(span + gid);
+        if (sp == 0) return;
+        u32 r = __ldg(tail_row + gid);
+        u32 cur[V];
+        load_vec_rw<V>(cur, y + (size_t)r * NP + sub * V);
+        u64 s[V];
+#pragma unroll
+        for (int k = 0; k < V; k++) s[k] = cur[k];
+        const u32 *w = whead + (size_t)(gid + 1) * NP + sub * V;
+#pragma unroll 4
+        for (u32 j = 0; j < sp; j++) {
+                u32 h[V];
+                load_vec_rw<V>(h, w + (size_t)j * NP);
+#pragma unroll
+                for (int k = 0; k < V; k++) s[k] += h[k];
+        }
+#pragma unroll
+        for (int k = 0; k < V; k++) cur[k] = mp_reduce(s[k], m);
+        store_vec<V>(y + (size_t)r * NP + sub * V, cur);
+}
+
+template <int L, int V>
+int launch_lv(const SpOp &op, const ModP &m, const u32 *x, u32 *y, const DevSmall *state, cudaStream_t st)
+{
+        unsigned blocks = (unsigned)((op.ntiles + WARPS - 1) / WARPS);
+        switch (m.fold_every) {
+        case 0: k_spmv<L, V, 0><<<blocks, WARPS * 32, 0, st>>>(op.ent, op.chunk_row, op.whead, op.ntiles, op.Q, (u32)op.rows, x, y, m, state); break;
+        case 8: k_spmv<L, V, 8><<<blocks, WARPS * 32, 0, st>>>(op.ent, op.chunk_row, op.whead, op.ntiles, op.Q, (u32)op.rows, x, y, m, state); break;
+        default: k_spmv<L, V, 2><<<blocks, WARPS * 32, 0, st>>>(op.ent, op.chunk_row, op.whead, op.ntiles, op.Q, (u32)op.rows, x, y, m, state); break;
+        }
+        int64_t threads = op.ntiles * L;
+        k_spmv_fix<L, V><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(op.tail_row, op.span, op.whead, op.ntiles, y, m, state);
+        return 2;
+}
+
+}  // namespace
+
+int launch_spmv(const SpOp &op, const Geometry &geo, const ModP &m, const u32 *x, u32 *y,
+                const DevSmall *state, cudaStream_t st)
+{
+        switch (geo.np) {
+        case 1: return launch_lv<1, 1>(op, m, x, y, state, st);
+        case 2: return launch_lv<1, 2>(op, m, x, y, state, st);
+        case 4: return launch_lv<1, 4>(op, m, x, y, state, st);
+        case 8: return launch_lv<2, 4>(op, m, x, y, state, st);
+        case 16: return launch_lv<4, 4>(op, m, x, y, state, st);
+        case 32: return launch_lv<8, 4>(op, m, x, y, state, st);
+        case 64: return launch_lv<16, 4>(op, m, x, y, state, st);
+        }
+        return -1;
+}
