@@ -83,18 +83,16 @@ int launch_spmv(const SpOp &op, const Geometry &geo, const ModP &m, const u32 *x
 
 // dense.cu
 int dots_num_blocks(int64_t rows, int np);
+// dots adds its per-block results (canonical residues) into the u64 accumulators sums[2*np*np]
 int launch_dots(const Geometry &geo, const ModP &m, int64_t rows, const u32 *v, const u32 *Av,
-                u32 *partials, int nblocks, const DevSmall *state, cudaStream_t st);
+                u64 *sums, int nblocks, const DevSmall *state, cudaStream_t st);
 // mats layout (u32, each np*np unless noted): [0] vtAv [1] vtAAv [2] winv [3] c [4] vtAvd [5] d (np)
 enum { MAT_VTAV = 0, MAT_VTAAV = 1, MAT_WINV = 2, MAT_C = 3, MAT_VTAVD = 4, MAT_D = 5, MAT_COUNT = 6 };
-// sums: if partials != nullptr the kernel adds `nblocks` partial blocks, else it reads the u64
-// array `sums` (2*np*np, e.g. after an all-reduce).  mode: 0 full iteration step (semi_inverse +
-// coefficients + flags), 1 only reduce dots into MAT_VTAV/MAT_VTAAV, 2 semi_inverse of MAT_VTAV
-// only, 3 coefficients from given MAT_D/MAT_WINV/MAT_VTAV/MAT_VTAAV.
-int launch_small(const Geometry &geo, const ModP &m, const u32 *partials, int nblocks, const u64 *sums,
-                 u32 *mats, DevSmall *state, int mode, cudaStream_t st);
-int launch_partials_to_sums(const Geometry &geo, const ModP &m, const u32 *partials, int nblocks,
-                            u64 *sums, const DevSmall *state, cudaStream_t st);
+// One block.  mode 0: full iteration step (reduce sums mod p and clear them, semi_inverse,
+// coefficients, loop flags); 1: only reduce sums into MAT_VTAV/MAT_VTAAV; 2: semi_inverse of
+// MAT_VTAV only; 3: coefficients from given MAT_D/MAT_WINV/MAT_VTAV/MAT_VTAAV.
+int launch_small(const Geometry &geo, const ModP &m, u64 *sums, u32 *mats, DevSmall *state, int mode,
+                 cudaStream_t st);
 int launch_ortho(const Geometry &geo, const ModP &m, int64_t rows, u32 *v, const u32 *Av, u32 *p,
                  u32 *v_out, u32 *p_out, const u32 *mats, const DevSmall *state, int force,
                  cudaStream_t st);

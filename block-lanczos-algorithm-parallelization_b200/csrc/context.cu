@@ -93,8 +93,8 @@ struct blk_ctx {
         SpOp S1, S2;                            // tmp <- S1 v ; Av <- S2 tmp
         u32 *v = nullptr, *tmp = nullptr;       // full length: N*np, Mc*np
         u32 *Av = nullptr, *p = nullptr;        // local rows [n0,n1) * np
-        u32 *partials = nullptr, *mats = nullptr;
-        u64 *sums = nullptr;
+        u32 *mats = nullptr;
+        u64 *sums = nullptr;                   // 2*np*np dot-product accumulators (zero between iterations)
         DevSmall *state = nullptr, *h_state = nullptr;
         int dots_blocks = 1;
         cudaStream_t stream = nullptr;
@@ -233,21 +233,16 @@ int enqueue_iteration(blk_ctx *c, EventTimer *tm)
         int64_t lrows = c->n1() - c->n0();
         u32 *vloc = c->v + (size_t)c->n0() * np;
         if (tm) tm->begin(c, BLK_PH_DOTS);
-        k = launch_dots(g, c->m, lrows, vloc, c->Av, c->partials, c->dots_blocks, c->state, c->stream);
+        k = launch_dots(g, c->m, lrows, vloc, c->Av, c->sums, c->dots_blocks, c->state, c->stream);
         c->launches += k;
         if (tm) tm->end(c, k);
         if (c->world > 1) {
                 if (tm) tm->begin(c, BLK_PH_EXCHANGE);
-                k = launch_partials_to_sums(g, c->m, c->partials, c->dots_blocks, c->sums, c->state, c->stream);
-                c->launches += k;
                 NC(g_nccl.AllReduce(c->sums, c->sums, (size_t)2 * np * np, ncclUint64, ncclSum, c->comm, c->stream));
-                if (tm) tm->end(c, k);
-                if (tm) tm->begin(c, BLK_PH_SMALL);
-                k = launch_small(g, c->m, nullptr, 0, c->sums, c->mats, c->state, 0, c->stream);
-        } else {
-                if (tm) tm->begin(c, BLK_PH_SMALL);
-                k = launch_small(g, c->m, c->partials, c->dots_blocks, nullptr, c->mats, c->state, 0, c->stream);
+                if (tm) tm->end(c, 0);
         }
+        if (tm) tm->begin(c, BLK_PH_SMALL);
+        k = launch_small(g, c->m, c->sums, c->mats, c->state, 0, c->stream);
         c->launches += k;
         if (tm) tm->end(c, k);
         if (tm) tm->begin(c, BLK_PH_ORTHO);
@@ -329,7 +324,7 @@ int build_graph(blk_ctx *c)
         return 0;
 }
 
-int kernels_per_iteration(const blk_ctx *c) { return c->world > 1 ? 8 : 7; }
+int kernels_per_iteration(const blk_ctx *) { return 7; }
 
 }  // namespace
 
@@ -377,7 +372,7 @@ int blk_destroy(blk_ctx *c)
         free_operator(&c->S1);
         free_operator(&c->S2);
         cudaFree(c->v); cudaFree(c->tmp); cudaFree(c->Av); cudaFree(c->p);
-        cudaFree(c->partials); cudaFree(c->mats); cudaFree(c->sums); cudaFree(c->state);
+        cudaFree(c->mats); cudaFree(c->sums); cudaFree(c->state);
         if (c->h_state) cudaFreeHost(c->h_state);
         if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
         delete c;
@@ -521,12 +516,12 @@ int blk_create(blk_ctx **out, const blk_params *prm)
         CUX(cudaMemsetAsync(c->Av, 0, bl, c->stream)); CUX(cudaMemsetAsync(c->p, 0, bl, c->stream));
         c->block_bytes = bv + bt + 2 * bl;
         c->dots_blocks = dots_num_blocks(ln, np);
-        CUX(cudaMalloc(&c->partials, sizeof(u32) * (size_t)c->dots_blocks * 2 * np * np));
         CUX(cudaMalloc(&c->mats, sizeof(u32) * (size_t)MAT_COUNT * np * np));
         CUX(cudaMalloc(&c->sums, sizeof(u64) * (size_t)2 * np * np));
         CUX(cudaMalloc(&c->state, sizeof(DevSmall)));
         CUX(cudaMallocHost(&c->h_state, sizeof(DevSmall)));
         CUX(cudaMemsetAsync(c->mats, 0, sizeof(u32) * (size_t)MAT_COUNT * np * np, c->stream));
+        CUX(cudaMemsetAsync(c->sums, 0, sizeof(u64) * (size_t)2 * np * np, c->stream));
         memset(c->h_state, 0, sizeof(DevSmall));
         c->h_state->halt = 1;
         if (push_state(c)) { blk_destroy(c); return 1; }
@@ -631,14 +626,15 @@ int blk_get_state(blk_ctx *c, uint32_t *v, uint32_t *tmp, uint32_t *Av, uint32_t
         if (c->world > 1 && allgather_rows(c, c->v, c->n_off)) return 1;
         std::vector<u32> hv;
         const u32 *vsrc = nullptr;
-        if (v || tmp) {
+        if (v) {
+                // straight into the caller's buffer (fast when it is pinned)
+                if (download_rows(c, v, c->v, N)) return 1;
+                memset(v + (size_t)N * n, 0, sizeof(u32) * (size_t)(pad - N * n));
+                vsrc = v;
+        } else if (tmp) {
                 hv.resize((size_t)N * n);
                 if (download_rows(c, hv.data(), c->v, N)) return 1;
                 vsrc = hv.data();
-        }
-        if (v) {
-                memset(v, 0, sizeof(u32) * (size_t)pad);
-                memcpy(v, vsrc, sizeof(u32) * (size_t)N * n);
         }
         if (tmp) {
                 // see DESIGN.md "tmp": the reference's tmp holds the next v in rows [0,N) after
@@ -740,17 +736,19 @@ int blk_block_dot_products(blk_ctx *c, uint32_t *vtAv, uint32_t *vtAAv, int64_t 
         if (!c || !vtAv || !vtAAv || !Av || !v || N < 0) return fail("blk_block_dot_products: bad argument");
         CU(cudaSetDevice(c->device));
         const int np = c->geo.np, n = c->geo.n;
-        u32 *dv = nullptr, *da = nullptr, *part = nullptr, *mats = nullptr;
+        u32 *dv = nullptr, *da = nullptr, *mats = nullptr;
+        u64 *sums = nullptr;
         int64_t rows = N > 0 ? N : 1;
         int nblocks = dots_num_blocks(N, np);
         CU(cudaMalloc(&dv, sizeof(u32) * (size_t)rows * np));
         CU(cudaMalloc(&da, sizeof(u32) * (size_t)rows * np));
-        CU(cudaMalloc(&part, sizeof(u32) * (size_t)nblocks * 2 * np * np));
+        CU(cudaMalloc(&sums, sizeof(u64) * (size_t)2 * np * np));
         CU(cudaMalloc(&mats, sizeof(u32) * (size_t)MAT_COUNT * np * np));
+        CU(cudaMemsetAsync(sums, 0, sizeof(u64) * (size_t)2 * np * np, c->stream));
         int rc = upload_rows(c, dv, v, N) || upload_rows(c, da, Av, N);
         if (!rc) {
-                c->launches += launch_dots(c->geo, c->m, N, dv, da, part, nblocks, nullptr, c->stream);
-                c->launches += launch_small(c->geo, c->m, part, nblocks, nullptr, mats, c->state, 1, c->stream);
+                c->launches += launch_dots(c->geo, c->m, N, dv, da, sums, nblocks, nullptr, c->stream);
+                c->launches += launch_small(c->geo, c->m, sums, mats, c->state, 1, c->stream);
                 std::vector<u32> h((size_t)2 * np * np);
                 cudaMemcpyAsync(h.data(), mats, sizeof(u32) * h.size(), cudaMemcpyDeviceToHost, c->stream);
                 cudaError_t e = cudaStreamSynchronize(c->stream);
@@ -762,7 +760,7 @@ int blk_block_dot_products(blk_ctx *c, uint32_t *vtAv, uint32_t *vtAAv, int64_t 
                                         vtAAv[i * n + j] = h[(size_t)MAT_VTAAV * np * np + i * np + j];
                                 }
         }
-        cudaFree(dv); cudaFree(da); cudaFree(part); cudaFree(mats);
+        cudaFree(dv); cudaFree(da); cudaFree(sums); cudaFree(mats);
         return rc;
 }
 
@@ -785,7 +783,7 @@ int blk_semi_inverse(blk_ctx *c, const uint32_t *M_, uint32_t *winv, uint32_t *d
         CU(cudaMalloc(&st, sizeof(DevSmall)));
         CU(cudaMemsetAsync(st, 0, sizeof(DevSmall), c->stream));
         CU(cudaMemcpyAsync(mats, h.data(), sizeof(u32) * h.size(), cudaMemcpyHostToDevice, c->stream));
-        c->launches += launch_small(c->geo, c->m, nullptr, 0, nullptr, mats, st, 2, c->stream);
+        c->launches += launch_small(c->geo, c->m, nullptr, mats, st, 2, c->stream);
         DevSmall hs;
         CU(cudaMemcpyAsync(h.data(), mats, sizeof(u32) * h.size(), cudaMemcpyDeviceToHost, c->stream));
         CU(cudaMemcpyAsync(&hs, st, sizeof(DevSmall), cudaMemcpyDeviceToHost, c->stream));
@@ -821,7 +819,7 @@ int blk_orthogonalize(blk_ctx *c, const uint32_t *v, uint32_t *tmp, uint32_t *p,
         CU(cudaMemcpyAsync(mats, h.data(), sizeof(u32) * h.size(), cudaMemcpyHostToDevice, c->stream));
         int rc = upload_rows(c, dv, v, N) || upload_rows(c, da, Av, N) || upload_rows(c, dp, p, N);
         if (!rc && N > 0) {
-                c->launches += launch_small(c->geo, c->m, nullptr, 0, nullptr, mats, c->state, 3, c->stream);
+                c->launches += launch_small(c->geo, c->m, nullptr, mats, c->state, 3, c->stream);
                 c->launches += launch_ortho(c->geo, c->m, N, dv, da, dp, dvo, dp, mats, c->state, 1, c->stream);
                 rc = download_rows(c, tmp, dvo, N) || download_rows(c, p, dp, N);
                 cudaError_t e = cudaGetLastError();

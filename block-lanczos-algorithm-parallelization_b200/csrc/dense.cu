@@ -38,11 +38,11 @@ template <int V> __device__ __forceinline__ void stv(u32 *p, const u32 (&o)[V])
 
 // ------------------------------------------------------------------------------------------
 // dots: a team of T = (NP/TI)^2 threads owns the NP x NP outputs (TI x TI register tile per
-// thread, for both matrices); teams stride over the rows.  partials[block][2][NP*NP], reduced.
+// thread, for both matrices); teams stride over the rows.  Block results are added to sums[2][NP*NP].
 // ------------------------------------------------------------------------------------------
 template <int NP, int FOLD>
 __global__ void __launch_bounds__(DOTS_TB)
-k_dots(int64_t rows, const u32 *__restrict__ v, const u32 *__restrict__ Av, u32 *__restrict__ partials,
+k_dots(int64_t rows, const u32 *__restrict__ v, const u32 *__restrict__ Av, unsigned long long *__restrict__ sums,
        ModP m, const DevSmall *__restrict__ state)
 {
         constexpr int TI = NP < 4 ? NP : 4;
@@ -84,14 +84,15 @@ k_dots(int64_t rows, const u32 *__restrict__ v, const u32 *__restrict__ Av, u32 
                 }
         }
 
-        u32 *out = partials + (size_t)blockIdx.x * 2 * NP * NP;
+        // block result -> global u64 sums (integer addition: order-free, hence deterministic).
+        // Every addend is a canonical residue < 2^31, so 2^33 blocks could not overflow.
         if (TEAMS == 1) {
 #pragma unroll
                 for (int a = 0; a < TI; a++)
 #pragma unroll
                         for (int b = 0; b < TI; b++) {
-                                out[(i0 + a) * NP + j0 + b] = mp_reduce(a1[a][b], m);
-                                out[NP * NP + (i0 + a) * NP + j0 + b] = mp_reduce(a2[a][b], m);
+                                atomicAdd(&sums[(i0 + a) * NP + j0 + b], (unsigned long long)mp_reduce(a1[a][b], m));
+                                atomicAdd(&sums[NP * NP + (i0 + a) * NP + j0 + b], (unsigned long long)mp_reduce(a2[a][b], m));
                         }
         } else {
                 __shared__ unsigned long long acc[TEAMS == 1 ? 1 : 2 * NP * NP];
@@ -105,19 +106,9 @@ k_dots(int64_t rows, const u32 *__restrict__ v, const u32 *__restrict__ Av, u32 
                                 atomicAdd(&acc[NP * NP + (i0 + a) * NP + j0 + b], (unsigned long long)mp_reduce(a2[a][b], m));
                         }
                 __syncthreads();
-                for (int e = tid; e < 2 * NP * NP; e += DOTS_TB) out[e] = mp_reduce(acc[e], m);
+                for (int e = tid; e < 2 * NP * NP; e += DOTS_TB)
+                        atomicAdd(&sums[e], (unsigned long long)mp_reduce(acc[e], m));
         }
-}
-
-__global__ void k_partials_to_sums(int np2x2, const u32 *__restrict__ partials, int nblocks,
-                                   u64 *__restrict__ sums, const DevSmall *__restrict__ state)
-{
-        if (state && state->halt) return;
-        int e = blockIdx.x * blockDim.x + threadIdx.x;
-        if (e >= np2x2) return;
-        u64 s = 0;
-        for (int b = 0; b < nblocks; b++) s += partials[(size_t)b * np2x2 + e];
-        sums[e] = s;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -125,101 +116,88 @@ __global__ void k_partials_to_sums(int np2x2, const u32 *__restrict__ partials, 
 // ------------------------------------------------------------------------------------------
 constexpr int SMALL_TB = 256;
 
-// Gauss-Jordan sweep shared by both phases of semi_inverse (sequential/lanczos_modp.c:351-382,
-// :393-436): first non-zero at or below the diagonal is the pivot, the pivot row is scaled to 1,
-// swapped into place, and column j is cleared in every other row.  W (may be null) receives the
-// same row operations.  Returns the number of pivots; d[j] = 1 on pivot columns.
-__device__ int gj_sweep(u32 *M, u32 *W, u32 *d, u32 *mult, int *ctl, int n, const ModP &m)
+struct GjBuf { u32 *M, *W, *scal; };
+
+// One Gauss-Jordan sweep of semi_inverse (sequential/lanczos_modp.c:351-382 and :393-436): for
+// each column j the FIRST row i >= j with a non-zero entry is the pivot; the reference scales that
+// row by the inverse of the pivot, swaps it into row j and clears column j in every other row.
+//
+// Done here fraction-free so that no modular inverse sits on the serial path: row i of the
+// working matrices is kept as scal[i] times the reference's row (scal[i] != 0), the update is
+//      row_i <- pv * row_i - row_i[j] * row_piv        scal[i] <- scal[i] * pv     (i != j)
+//      row_j <- row_piv                                scal[j] <- pv
+// Zero patterns -- and therefore every pivot decision -- are identical to the reference's, and
+// dividing row i by scal[i] at the end (n independent inverses, one per thread) gives exactly
+// the reference's W.  Double buffered in shared memory: one barrier per pivot column.
+// Returns the number of pivots; d[j] = 1 on pivot columns; *cur = buffer holding the result.
+__device__ int gj_sweep(GjBuf *buf, int *cur, bool carry_w, u32 *d, int n, const ModP &m)
 {
         const int tid = threadIdx.x;
-        int found = 0;
-        for (int j = tid; j < n; j += SMALL_TB) d[j] = 0;
-        __syncthreads();
+        int found = 0, s = *cur;
         for (int j = 0; j < n; j++) {
-                if (tid < 32) {
-                        // rows tid and tid+32
-                        bool h0 = (tid >= j && tid < n) ? M[tid * n + j] != 0 : false;
-                        bool h1 = (tid + 32 >= j && tid + 32 < n) ? M[(tid + 32) * n + j] != 0 : false;
-                        unsigned b0 = __ballot_sync(0xffffffffu, h0), b1 = __ballot_sync(0xffffffffu, h1);
-                        if (tid == 0) {
-                                int piv = b0 ? __ffs(b0) - 1 : (b1 ? 32 + __ffs(b1) - 1 : -1);
-                                ctl[0] = piv;
-                                if (piv >= 0) ctl[1] = (int)mp_inv(M[piv * n + j], m);
-                        }
-                }
-                __syncthreads();
-                const int piv = ctl[0];
-                if (piv < 0) { __syncthreads(); continue; }
-                const u32 inv = (u32)ctl[1];
+                const u32 *Ms = buf[s].M, *Ws = buf[s].W, *ss = buf[s].scal;
+                u32 *Md = buf[s ^ 1].M, *Wd = buf[s ^ 1].W, *sd = buf[s ^ 1].scal;
+                int piv = -1;
+                for (int i = j; i < n; i++)
+                        if (Ms[i * n + j] != 0) { piv = i; break; }       // same answer in every thread
+                if (tid == 0) d[j] = piv >= 0;
+                if (piv < 0) continue;
                 found++;
-                for (int k = tid; k < n; k += SMALL_TB) {
-                        u32 a = mp_mul(M[piv * n + k], inv, m);
-                        M[piv * n + k] = M[j * n + k];
-                        M[j * n + k] = a;
-                        if (W) {
-                                u32 b = mp_mul(W[piv * n + k], inv, m);
-                                W[piv * n + k] = W[j * n + k];
-                                W[j * n + k] = b;
+                const u32 pv = Ms[piv * n + j];
+                for (int e = tid; e < n * n; e += SMALL_TB) {
+                        const int i = e / n, k = e - i * n;
+                        if (i == j) {
+                                Md[e] = Ms[piv * n + k];
+                                if (carry_w) Wd[e] = Ws[piv * n + k];
+                        } else {
+                                const int r = (i == piv) ? j : i;           // row i after the swap
+                                const u32 f = mp_neg(Ms[r * n + j], m);
+                                Md[e] = mp_reduce((u64)pv * Ms[r * n + k] + (u64)f * Ms[piv * n + k], m);
+                                if (carry_w) Wd[e] = mp_reduce((u64)pv * Ws[r * n + k] + (u64)f * Ws[piv * n + k], m);
                         }
                 }
-                if (tid == 0) d[j] = 1;
+                if (carry_w)
+                        for (int i = tid; i < n; i += SMALL_TB) {
+                                const int r = (i == piv) ? j : i;
+                                sd[i] = (i == j) ? pv : mp_mul(ss[r], pv, m);
+                        }
                 __syncthreads();
-                for (int i = tid; i < n; i += SMALL_TB) mult[i] = (i == j) ? 0u : mp_neg(M[i * n + j], m);
-                __syncthreads();
-                for (int e = tid; e < n * n; e += SMALL_TB) {
-                        int i = e / n, k = e - i * n;
-                        if (i == j) continue;
-                        u32 f = mult[i];
-                        if (f == 0) continue;
-                        M[e] = mp_reduce((u64)M[e] + (u64)f * M[j * n + k], m);
-                        if (W) W[e] = mp_reduce((u64)W[e] + (u64)f * W[j * n + k], m);
-                }
-                __syncthreads();
+                s ^= 1;
         }
+        *cur = s;
         return found;
 }
 
 // mode 0: full step; 1: reduce dots only; 2: semi_inverse of mats[VTAV]; 3: coefficients only
 __global__ void __launch_bounds__(SMALL_TB)
-k_small(int n, int np, const u32 *__restrict__ partials, int nblocks, const u64 *__restrict__ sums,
-        u32 *__restrict__ mats, DevSmall *__restrict__ state, int mode, ModP m)
+k_small(int n, int np, unsigned long long *__restrict__ sums, u32 *__restrict__ mats,
+        DevSmall *__restrict__ state, int mode, ModP m)
 {
         extern __shared__ u32 sm[];
         const int tid = threadIdx.x;
         const int nn = n * n, npp = np * np;
         u32 *A = sm;               // vtAv   (n x n)
         u32 *B = A + nn;           // vtAAv
-        u32 *M = B + nn;           // elimination work matrix
-        u32 *W = M + nn;           // winv
-        u32 *d = W + nn;           // n
+        GjBuf buf[2];
+        buf[0].M = B + nn;   buf[0].W = buf[0].M + nn;
+        buf[1].M = buf[0].W + nn; buf[1].W = buf[1].M + nn;
+        buf[0].scal = buf[1].W + nn; buf[1].scal = buf[0].scal + n;
+        u32 *d = buf[1].scal + n;  // n
         u32 *d1 = d + n;           // n (phase-1 pivots)
-        u32 *mult = d1 + n;        // n
-        int *ctl = (int *)(mult + n);
 
         if (mode == 0 && state->halt) {
                 if (tid == 0) state->do_ortho = 0;
                 return;
         }
 
-        // ---- gather the dot products
+        // ---- gather the dot products (and clear the accumulators for the next iteration)
         if (mode <= 1) {
-                for (int e = tid; e < 2 * nn; e += SMALL_TB) {
-                        int which = e / nn, r = e - which * nn;
-                        int i = r / n, j = r - i * n;
-                        int src = which * npp + i * np + j;
-                        u64 s = 0;
-                        if (partials) {
-                                for (int b = 0; b < nblocks; b++) s += partials[(size_t)b * 2 * npp + src];
-                        } else {
-                                s = sums[src];
-                        }
-                        (which ? B : A)[r] = mp_reduce(s, m);
-                }
-                __syncthreads();
                 for (int e = tid; e < 2 * npp; e += SMALL_TB) {
                         int which = e / npp, r = e - which * npp;
                         int i = r / np, j = r - i * np;
-                        u32 val = (i < n && j < n) ? (which ? B : A)[i * n + j] : 0u;
+                        u32 val = mp_reduce(sums[e], m);
+                        sums[e] = 0;
+                        if (i < n && j < n) (which ? B : A)[i * n + j] = val;
                         mats[(which ? MAT_VTAAV : MAT_VTAV) * npp + r] = val;
                 }
                 if (mode == 1) return;
@@ -233,20 +211,31 @@ k_small(int n, int np, const u32 *__restrict__ partials, int nblocks, const u64 
         __syncthreads();
 
         int npiv = 0;
+        u32 *W = buf[0].W;
         if (mode == 0 || mode == 2) {
                 // ---- semi_inverse, phase 1: which columns carry a pivot
-                for (int e = tid; e < nn; e += SMALL_TB) M[e] = A[e];
+                int cur = 0;
+                for (int e = tid; e < nn; e += SMALL_TB) buf[0].M[e] = A[e];
                 __syncthreads();
-                gj_sweep(M, nullptr, d1, mult, ctl, n, m);
+                gj_sweep(buf, &cur, false, d1, n, m);
+                __syncthreads();
                 // ---- phase 2 on the d x d restriction, carrying winv along
                 for (int e = tid; e < nn; e += SMALL_TB) {
                         int i = e / n, j = e - i * n;
                         bool keep = d1[i] && d1[j];
-                        M[e] = keep ? A[e] : 0u;
-                        W[e] = (i == j && d1[i]) ? 1u : 0u;
+                        buf[cur].M[e] = keep ? A[e] : 0u;
+                        buf[cur].W[e] = (i == j && d1[i]) ? 1u : 0u;
                 }
+                for (int i = tid; i < n; i += SMALL_TB) buf[cur].scal[i] = 1u;
                 __syncthreads();
-                npiv = gj_sweep(M, W, d, mult, ctl, n, m);
+                npiv = gj_sweep(buf, &cur, true, d, n, m);
+                __syncthreads();
+                // undo the row scalings: n independent inverses, one per thread
+                for (int i = tid; i < n; i += SMALL_TB) buf[cur].scal[i] = mp_inv(buf[cur].scal[i], m);
+                __syncthreads();
+                W = buf[cur].W;
+                for (int e = tid; e < nn; e += SMALL_TB) W[e] = mp_mul(W[e], buf[cur].scal[e / n], m);
+                __syncthreads();
                 for (int e = tid; e < npp; e += SMALL_TB) {
                         int i = e / np, j = e - i * np;
                         mats[MAT_WINV * npp + e] = (i < n && j < n) ? W[i * n + j] : 0u;
@@ -413,13 +402,13 @@ __global__ void k_unpad_rows(const u32 *__restrict__ src, u32 *__restrict__ dst,
 }
 
 template <int NP>
-int dots_fold(const ModP &m, int64_t rows, const u32 *v, const u32 *Av, u32 *partials, int nblocks,
+int dots_fold(const ModP &m, int64_t rows, const u32 *v, const u32 *Av, u64 *sums, int nblocks,
               const DevSmall *state, cudaStream_t st)
 {
         switch (m.fold_every) {
-        case 0: k_dots<NP, 0><<<nblocks, DOTS_TB, 0, st>>>(rows, v, Av, partials, m, state); break;
-        case 8: k_dots<NP, 8><<<nblocks, DOTS_TB, 0, st>>>(rows, v, Av, partials, m, state); break;
-        default: k_dots<NP, 2><<<nblocks, DOTS_TB, 0, st>>>(rows, v, Av, partials, m, state); break;
+        case 0: k_dots<NP, 0><<<nblocks, DOTS_TB, 0, st>>>(rows, v, Av, (unsigned long long *)sums, m, state); break;
+        case 8: k_dots<NP, 8><<<nblocks, DOTS_TB, 0, st>>>(rows, v, Av, (unsigned long long *)sums, m, state); break;
+        default: k_dots<NP, 2><<<nblocks, DOTS_TB, 0, st>>>(rows, v, Av, (unsigned long long *)sums, m, state); break;
         }
         return 1;
 }
@@ -465,33 +454,25 @@ int dots_num_blocks(int64_t rows, int np)
 }
 
 int launch_dots(const Geometry &geo, const ModP &m, int64_t rows, const u32 *v, const u32 *Av,
-                u32 *partials, int nblocks, const DevSmall *state, cudaStream_t st)
+                u64 *sums, int nblocks, const DevSmall *state, cudaStream_t st)
 {
         switch (geo.np) {
-        case 1: return dots_fold<1>(m, rows, v, Av, partials, nblocks, state, st);
-        case 2: return dots_fold<2>(m, rows, v, Av, partials, nblocks, state, st);
-        case 4: return dots_fold<4>(m, rows, v, Av, partials, nblocks, state, st);
-        case 8: return dots_fold<8>(m, rows, v, Av, partials, nblocks, state, st);
-        case 16: return dots_fold<16>(m, rows, v, Av, partials, nblocks, state, st);
-        case 32: return dots_fold<32>(m, rows, v, Av, partials, nblocks, state, st);
-        case 64: return dots_fold<64>(m, rows, v, Av, partials, nblocks, state, st);
+        case 1: return dots_fold<1>(m, rows, v, Av, sums, nblocks, state, st);
+        case 2: return dots_fold<2>(m, rows, v, Av, sums, nblocks, state, st);
+        case 4: return dots_fold<4>(m, rows, v, Av, sums, nblocks, state, st);
+        case 8: return dots_fold<8>(m, rows, v, Av, sums, nblocks, state, st);
+        case 16: return dots_fold<16>(m, rows, v, Av, sums, nblocks, state, st);
+        case 32: return dots_fold<32>(m, rows, v, Av, sums, nblocks, state, st);
+        case 64: return dots_fold<64>(m, rows, v, Av, sums, nblocks, state, st);
         }
         return -1;
 }
 
-int launch_partials_to_sums(const Geometry &geo, const ModP &, const u32 *partials, int nblocks,
-                            u64 *sums, const DevSmall *state, cudaStream_t st)
+int launch_small(const Geometry &geo, const ModP &m, u64 *sums, u32 *mats, DevSmall *state, int mode,
+                 cudaStream_t st)
 {
-        int cnt = 2 * geo.np * geo.np;
-        k_partials_to_sums<<<(cnt + 255) / 256, 256, 0, st>>>(cnt, partials, nblocks, sums, state);
-        return 1;
-}
-
-int launch_small(const Geometry &geo, const ModP &m, const u32 *partials, int nblocks, const u64 *sums,
-                 u32 *mats, DevSmall *state, int mode, cudaStream_t st)
-{
-        size_t smem = sizeof(u32) * (4 * (size_t)geo.n * geo.n + 3 * geo.n + 8);
-        k_small<<<1, SMALL_TB, smem, st>>>(geo.n, geo.np, partials, nblocks, sums, mats, state, mode, m);
+        size_t smem = sizeof(u32) * (6 * (size_t)geo.n * geo.n + 4 * geo.n + 8);
+        k_small<<<1, SMALL_TB, smem, st>>>(geo.n, geo.np, (unsigned long long *)sums, mats, state, mode, m);
         return 1;
 }
 
@@ -512,7 +493,7 @@ int launch_ortho(const Geometry &geo, const ModP &m, int64_t rows, u32 *v, const
 
 void dense_prepare(const Geometry &geo, const ModP &m)
 {
-        cudaFuncSetAttribute(k_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(k_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
         launch_ortho(geo, m, -1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr);
 }
 
