@@ -27,7 +27,7 @@ PHASES = ("spmv1", "spmv2", "dots", "small", "ortho", "exchange")
 # every symbol include/blk_lanczos.h declares
 ABI_SYMBOLS = (
     "blk_abi_version", "blk_last_error", "blk_device_count", "blk_nccl_unique_id", "blk_create",
-    "blk_destroy", "blk_block_pad", "blk_set_state", "blk_iterate", "blk_get_state", "blk_get_small",
+    "blk_destroy", "blk_plan_shards", "blk_block_pad", "blk_set_state", "blk_iterate", "blk_get_state", "blk_get_small",
     "blk_spmv", "blk_block_dot_products", "blk_semi_inverse", "blk_orthogonalize",
     "blk_set_profiling", "blk_get_phase_times", "blk_time_spmv", "blk_kernel_launches", "blk_get_info",
 )
@@ -76,6 +76,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.blk_nccl_unique_id.argtypes = [vp]
     L.blk_create.argtypes = [C.POINTER(vp), C.POINTER(blk_params)]
     L.blk_destroy.argtypes = [vp]
+    L.blk_plan_shards.argtypes = [vp, i64, i64, i32, vp]
     L.blk_block_pad.argtypes = [i32, i32, i32, i32]
     L.blk_block_pad.restype = i64
     L.blk_set_state.argtypes = [vp, vp, vp, i32]
@@ -109,6 +110,16 @@ def _ptr(a) -> C.c_void_p:
 
 def block_pad(nrows: int, ncols: int, n: int, right: bool) -> int:
     return int(load_library().blk_block_pad(nrows, ncols, n, int(right)))
+
+
+def plan_shards(idx, dim: int, world: int) -> np.ndarray:
+    """Row-block boundaries (world+1 offsets) blk_create uses along one dimension (host only)."""
+    L = load_library()
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    off = np.zeros(world + 1, dtype=np.int64)
+    if L.blk_plan_shards(_ptr(idx), idx.size, dim, world, _ptr(off)):
+        raise BlkError(L.blk_last_error().decode())
+    return off
 
 
 def nccl_unique_id() -> bytes:

@@ -17,6 +17,7 @@
 #include <nccl.h>
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "../../include/blk_lanczos.h"
@@ -355,6 +356,19 @@ int blk_nccl_unique_id(void *id_out)
         return 0;
 }
 
+int blk_plan_shards(const int32_t *idx, int64_t nnz, int64_t dim, int32_t world, int64_t *offsets)
+{
+        if (!offsets || dim < 0 || world < 1 || (nnz > 0 && !idx)) return fail("blk_plan_shards: bad argument");
+        std::vector<u32> cnt((size_t)dim, 0);
+        for (int64_t s = 0; s < nnz; s++) {
+                if (idx[s] < 0 || idx[s] >= dim) return fail("blk_plan_shards: index out of range");
+                cnt[(size_t)idx[s]]++;
+        }
+        std::vector<int64_t> off = partition_rows(cnt, world);
+        for (int r = 0; r <= world; r++) offsets[r] = off[r];
+        return 0;
+}
+
 int64_t blk_block_pad(int32_t nrows, int32_t ncols, int32_t n, int32_t right_kernel)
 {
         int64_t N = right_kernel ? ncols : nrows, Mc = right_kernel ? nrows : ncols;
@@ -420,6 +434,7 @@ int blk_create(blk_ctx **out, const blk_params *prm)
         else { CUX(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
 
         dense_prepare(c->geo, c->m);
+        if (const char *e = getenv("BLK_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
 
         // ---- COO on the device
         const int64_t nnz = prm->nnz;

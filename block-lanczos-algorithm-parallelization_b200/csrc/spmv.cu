@@ -10,6 +10,7 @@
 // gather of the x row (V*4 bytes per lane, n_pad*4 contiguous bytes per group).  U steps are
 // software-unrolled so that U independent gathers are in flight per lane.
 // HBM bytes per entry: 8 (matrix) + 4*n_pad (x row, when x does not fit L2) -- see DESIGN.md.
+#include <cstdlib>
 #include "blk_internal.cuh"
 
 namespace {
@@ -22,12 +23,24 @@ template <> struct Vec<1> { typedef unsigned int T; };
 template <> struct Vec<2> { typedef uint2 T; };
 template <> struct Vec<4> { typedef uint4 T; };
 
-template <int V> __device__ __forceinline__ void load_vec(u32 (&o)[V], const u32 *p)
+// Gather of one x row segment.  LD selects the cache policy (tuning knob BLK_GATHER_MODE):
+//   0 ld.global.nc   1 ld.global.cg (L2 only)   2 ld.global.nc.L1::no_allocate
+//   3 ld.global.nc.L1::no_allocate.L2::64B
+template <int V, int LD> __device__ __forceinline__ void load_vec(u32 (&o)[V], const u32 *p)
 {
-        typename Vec<V>::T t = __ldg(reinterpret_cast<const typename Vec<V>::T *>(p));
-        const u32 *w = reinterpret_cast<const u32 *>(&t);
+        if (V == 4) {
+                u32 a, b, c, d;
+                if (LD == 1) asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p));
+                else if (LD == 2) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p));
+                else if (LD == 3) asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p));
+                else asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p));
+                o[0] = a; o[1 % V] = b; o[2 % V] = c; o[3 % V] = d;
+        } else {
+                typename Vec<V>::T t = __ldg(reinterpret_cast<const typename Vec<V>::T *>(p));
+                const u32 *w = reinterpret_cast<const u32 *>(&t);
 #pragma unroll
-        for (int k = 0; k < V; k++) o[k] = w[k];
+                for (int k = 0; k < V; k++) o[k] = w[k];
+        }
 }
 template <int V> __device__ __forceinline__ void load_vec_rw(u32 (&o)[V], const u32 *p)
 {
@@ -45,7 +58,7 @@ template <int V> __device__ __forceinline__ void store_vec(u32 *p, const u32 (&o
         *reinterpret_cast<typename Vec<V>::T *>(p) = t;
 }
 
-template <int L, int V, int FOLD>
+template <int L, int V, int FOLD, int LD>
 __global__ void __launch_bounds__(WARPS * 32)
 k_spmv(const uint2 *__restrict__ ent, const u32 *__restrict__ chunk_row, u32 *__restrict__ whead,
        int64_t ntiles, int Q, u32 rows, const u32 *__restrict__ x, u32 *__restrict__ y, ModP m,
@@ -80,7 +93,7 @@ k_spmv(const uint2 *__restrict__ ent, const u32 *__restrict__ chunk_row, u32 *__
                 u32 xv[U][V];
 #pragma unroll
                 for (int u = 0; u < U; u++)
-                        load_vec<V>(xv[u], xs + (size_t)(ee[u].x & 0x7fffffffu) * NP);
+                        load_vec<V, LD>(xv[u], xs + (size_t)(ee[u].x & 0x7fffffffu) * NP);
 #pragma unroll
                 for (int u = 0; u < U; u++) {
 #pragma unroll
@@ -186,14 +199,40 @@ k_spmv_fix(const u32 *__restrict__ tail_row, const u32 *__restrict__ span, const
         store_vec<V>(y + (size_t)r * NP + sub * V, cur);
 }
 
-template <int L, int V>
-int launch_lv(const SpOp &op, const ModP &m, const u32 *x, u32 *y, const DevSmall *state, cudaStream_t st)
+template <int L, int V, int LD>
+void launch_ld(const SpOp &op, const ModP &m, const u32 *x, u32 *y, const DevSmall *state, cudaStream_t st)
 {
         unsigned blocks = (unsigned)((op.ntiles + WARPS - 1) / WARPS);
         switch (m.fold_every) {
-        case 0: k_spmv<L, V, 0><<<blocks, WARPS * 32, 0, st>>>(op.ent, op.chunk_row, op.whead, op.ntiles, op.Q, (u32)op.rows, x, y, m, state); break;
-        case 8: k_spmv<L, V, 8><<<blocks, WARPS * 32, 0, st>>>(op.ent, op.chunk_row, op.whead, op.ntiles, op.Q, (u32)op.rows, x, y, m, state); break;
-        default: k_spmv<L, V, 2><<<blocks, WARPS * 32, 0, st>>>(op.ent, op.chunk_row, op.whead, op.ntiles, op.Q, (u32)op.rows, x, y, m, state); break;
+        case 0: k_spmv<L, V, 0, LD><<<blocks, WARPS * 32, 0, st>>>(op.ent, op.chunk_row, op.whead, op.ntiles, op.Q, (u32)op.rows, x, y, m, state); break;
+        case 8: k_spmv<L, V, 8, LD><<<blocks, WARPS * 32, 0, st>>>(op.ent, op.chunk_row, op.whead, op.ntiles, op.Q, (u32)op.rows, x, y, m, state); break;
+        default: k_spmv<L, V, 2, LD><<<blocks, WARPS * 32, 0, st>>>(op.ent, op.chunk_row, op.whead, op.ntiles, op.Q, (u32)op.rows, x, y, m, state); break;
+        }
+}
+
+int gather_mode()
+{
+        static int mode = -1;
+        if (mode < 0) {
+                const char *e = getenv("BLK_GATHER_MODE");
+                mode = e ? atoi(e) : 0;
+                if (mode < 0 || mode > 3) mode = 0;
+        }
+        return mode;
+}
+
+template <int L, int V>
+int launch_lv(const SpOp &op, const ModP &m, const u32 *x, u32 *y, const DevSmall *state, cudaStream_t st)
+{
+        if (V == 4) {
+                switch (gather_mode()) {
+                case 1: launch_ld<L, V, 1>(op, m, x, y, state, st); break;
+                case 2: launch_ld<L, V, 2>(op, m, x, y, state, st); break;
+                case 3: launch_ld<L, V, 3>(op, m, x, y, state, st); break;
+                default: launch_ld<L, V, 0>(op, m, x, y, state, st); break;
+                }
+        } else {
+                launch_ld<L, V, 0>(op, m, x, y, state, st);
         }
         int64_t threads = op.ntiles * L;
         k_spmv_fix<L, V><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(op.tail_row, op.span, op.whead, op.ntiles, y, m, state);

