@@ -18,8 +18,6 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    ident = [B.nccl_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(ident, src=0)
     O = Oracle()
     cases = [
         (B.synth.powerlaw_rows(3000, 2700, mean=9, seed=3, with_empty_rows=11), 4, 65537, False, 9),
@@ -29,6 +27,8 @@ def main():
     for ci, (M, n, p, right, stop_after) in enumerate(cases):
         Mp = M.reduced(p)
         N = M.ncols if right else M.nrows
+        ident = [B.nccl_unique_id() if rank == 0 else None]      # one id per communicator
+        dist.broadcast_object_list(ident, src=0)
         ctx = B.BlockLanczos(Mp, n=n, prime=p, right=right, device=local, rank=rank, world=world, nccl_id=ident[0])
         info = ctx.info()
         assert (info["local_N0"], info["local_N1"]) != (0, N) or world == 1
