@@ -83,9 +83,17 @@ int launch_spmv(const SpOp &op, const Geometry &geo, const ModP &m, const u32 *x
 
 // dense.cu
 int dots_num_blocks(int64_t rows, int np);
+// When `counter` is non-null the dot-product kernel's last block to finish also runs the n x n
+// stage (k_small mode 0) -- one launch less per iteration (single-GPU loop only).
+struct SmallFuse {
+        unsigned *counter = nullptr;
+        u32 *mats = nullptr;
+        DevSmall *state = nullptr;
+        int n = 0;
+};
 // dots adds its per-block results (canonical residues) into the u64 accumulators sums[2*np*np]
 int launch_dots(const Geometry &geo, const ModP &m, int64_t rows, const u32 *v, const u32 *Av,
-                u64 *sums, int nblocks, const DevSmall *state, cudaStream_t st);
+                u64 *sums, int nblocks, const DevSmall *state, const SmallFuse &fuse, cudaStream_t st);
 // mats layout (u32, each np*np unless noted): [0] vtAv [1] vtAAv [2] winv [3] c [4] vtAvd [5] d (np)
 enum { MAT_VTAV = 0, MAT_VTAAV = 1, MAT_WINV = 2, MAT_C = 3, MAT_VTAVD = 4, MAT_D = 5, MAT_COUNT = 6 };
 // One block.  mode 0: full iteration step (reduce sums mod p and clear them, semi_inverse,
@@ -96,6 +104,20 @@ int launch_small(const Geometry &geo, const ModP &m, u64 *sums, u32 *mats, DevSm
 int launch_ortho(const Geometry &geo, const ModP &m, int64_t rows, u32 *v, const u32 *Av, u32 *p,
                  u32 *v_out, u32 *p_out, const u32 *mats, const DevSmall *state, int force,
                  cudaStream_t st);
+// dense_mma.cu: int8 tensor-core versions of dots / ortho for n_pad in {8,16,32}.  The ortho
+// kernel reads its right-hand operands from `bfrag`, stored behind the MAT_COUNT matrices of
+// `mats` in MMA fragment order (written by k_small): word index
+//   ((((X*4 + b)*T + t)*S + s)*32 + lane)*2 + h,   X in {c, vtAvd, winv}, T = S = np/8,
+// holding, for byte beta = 0..3, limb b of (2^(8 beta) * X[w][j] mod p) with j = 8t + (lane>>2)
+// and w = (lane&3)*np/4 + 2s + h.
+bool dense_mma_supported(int np);
+void dense_mma_prepare(int np);
+static inline size_t bfrag_words(int np) { return (np >= 8 && np <= 32) ? (size_t)12 * (np / 8) * (np / 8) * 64 : 0; }
+static inline size_t mats_words(int np) { return (size_t)MAT_COUNT * np * np + bfrag_words(np); }
+int launch_ortho_mma(int np, const ModP &m, int64_t rows, u32 *v, const u32 *Av, u32 *p, u32 *v_out, u32 *p_out,
+                     const u32 *mats, const DevSmall *state, int force, cudaStream_t st);
+int launch_dots_mma(int np, const ModP &m, int64_t rows, const u32 *v, const u32 *Av, u64 *sums,
+                    const DevSmall *state, const SmallFuse &fuse, cudaStream_t st);
 // per-device one-time kernel attributes (call with the device current, outside stream capture)
 void dense_prepare(const Geometry &geo, const ModP &m);
 // n <-> n_pad repacking of row-major blocks (rows x n  <->  rows x np)

@@ -47,6 +47,7 @@ struct NcclApi {
         ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
         ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
         ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+        ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
         ncclResult_t (*GroupStart)() = nullptr;
         ncclResult_t (*GroupEnd)() = nullptr;
         const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -67,6 +68,7 @@ bool nccl_load(std::string *why)
         SYM(CommDestroy, "ncclCommDestroy")
         SYM(AllReduce, "ncclAllReduce")
         SYM(Broadcast, "ncclBroadcast")
+        SYM(AllGather, "ncclAllGather")
         SYM(GroupStart, "ncclGroupStart")
         SYM(GroupEnd, "ncclGroupEnd")
         SYM(GetErrorString, "ncclGetErrorString")
@@ -96,11 +98,14 @@ struct blk_ctx {
         u32 *Av = nullptr, *p = nullptr;        // local rows [n0,n1) * np
         u32 *mats = nullptr;
         u64 *sums = nullptr;                   // 2*np*np dot-product accumulators (zero between iterations)
+        unsigned *dots_counter = nullptr;      // last-block-done ticket of the fused dots + small kernel
+        bool fuse_small = false;
         DevSmall *state = nullptr, *h_state = nullptr;
         int dots_blocks = 1;
         cudaStream_t stream = nullptr;
         bool own_stream = false;
         ncclComm_t comm = nullptr;
+        ncclResult_t (*nccl_allgather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
         // loop bookkeeping
         int iters = 0, stopped = 0;
         bool tmp_is_spmv = false;               // tmp rows [0,Mc) hold S1*v of the current v (stop case)
@@ -153,11 +158,15 @@ struct EventTimer {
         }
 };
 
-// weight-balanced contiguous partition of `dim` rows into `world` blocks
+// Contiguous partition of `dim` rows into `world` blocks.  Equal blocks (ceil(dim/world) rows, the
+// last one short) are preferred because the exchange is then a true in-place ncclAllGather; when
+// that would leave some rank more than 5% heavier (weight = non-zeros + 8 per row) than a
+// weight-balanced split, the weight-balanced boundaries are used and the all-gather becomes a
+// group of broadcasts.
 std::vector<int64_t> partition_rows(const std::vector<u32> &cnt, int world)
 {
         int64_t dim = (int64_t)cnt.size();
-        std::vector<int64_t> off(world + 1, 0);
+        std::vector<int64_t> off(world + 1, 0), eq(world + 1, 0);
         long double total = 0;
         for (int64_t r = 0; r < dim; r++) total += (long double)cnt[r] + 8.0L;
         long double run = 0;
@@ -168,7 +177,37 @@ std::vector<int64_t> partition_rows(const std::vector<u32> &cnt, int world)
         }
         while (k < world) off[k++] = dim;
         off[world] = dim;
+        int64_t R = (dim + world - 1) / world;
+        for (int q = 0; q <= world; q++) eq[q] = std::min<int64_t>(dim, (int64_t)q * R);
+        auto heaviest = [&](const std::vector<int64_t> &o) {
+                long double worst = 0;
+                for (int q = 0; q < world; q++) {
+                        long double w = 0;
+                        for (int64_t r = o[q]; r < o[q + 1]; r++) w += (long double)cnt[r] + 8.0L;
+                        worst = std::max(worst, w);
+                }
+                return worst;
+        };
+        if (world > 1 && heaviest(eq) <= 1.05L * heaviest(off)) return eq;
         return off;
+}
+
+// rows a buffer must hold to be the target of allgather_rows (equal blocks are padded)
+int64_t gather_cap(const std::vector<int64_t> &off)
+{
+        int world = (int)off.size() - 1;
+        int64_t dim = off[world], R = off[1] - off[0];
+        return std::max<int64_t>(dim, R * world);
+}
+
+bool equal_blocks(const std::vector<int64_t> &off)
+{
+        int world = (int)off.size() - 1;
+        int64_t dim = off[world], R = off[1] - off[0];
+        if (R <= 0) return false;
+        for (int q = 0; q <= world; q++)
+                if (off[q] != std::min<int64_t>(dim, (int64_t)q * R)) return false;
+        return true;
 }
 
 __global__ void k_count_rows(int64_t nnz, const int32_t *__restrict__ idx, int64_t dim, u32 *__restrict__ cnt)
@@ -194,8 +233,14 @@ __global__ void k_select_range(int64_t nnz, const int32_t *__restrict__ key, con
 
 inline unsigned nb(int64_t n) { return (unsigned)((n + 255) / 256); }
 
+// buf holds gather_cap(off) rows; every rank contributes rows [off[rank], off[rank+1]) in place
 int allgather_rows(blk_ctx *c, u32 *buf, const std::vector<int64_t> &off)
 {
+        if (c->nccl_allgather && equal_blocks(off)) {
+                size_t cnt = (size_t)(off[1] - off[0]) * c->geo.np;
+                NC(c->nccl_allgather(buf + (size_t)c->rank * cnt, buf, cnt, ncclUint32, c->comm, c->stream));
+                return 0;
+        }
         NC(g_nccl.GroupStart());
         for (int r = 0; r < c->world; r++) {
                 size_t cnt = (size_t)(off[r + 1] - off[r]) * c->geo.np;
@@ -234,7 +279,9 @@ int enqueue_iteration(blk_ctx *c, EventTimer *tm)
         int64_t lrows = c->n1() - c->n0();
         u32 *vloc = c->v + (size_t)c->n0() * np;
         if (tm) tm->begin(c, BLK_PH_DOTS);
-        k = launch_dots(g, c->m, lrows, vloc, c->Av, c->sums, c->dots_blocks, c->state, c->stream);
+        SmallFuse fuse;
+        if (c->fuse_small) { fuse.counter = c->dots_counter; fuse.mats = c->mats; fuse.state = c->state; fuse.n = g.n; }
+        k = launch_dots(g, c->m, lrows, vloc, c->Av, c->sums, c->dots_blocks, c->state, fuse, c->stream);
         c->launches += k;
         if (tm) tm->end(c, k);
         if (c->world > 1) {
@@ -242,10 +289,12 @@ int enqueue_iteration(blk_ctx *c, EventTimer *tm)
                 NC(g_nccl.AllReduce(c->sums, c->sums, (size_t)2 * np * np, ncclUint64, ncclSum, c->comm, c->stream));
                 if (tm) tm->end(c, 0);
         }
-        if (tm) tm->begin(c, BLK_PH_SMALL);
-        k = launch_small(g, c->m, c->sums, c->mats, c->state, 0, c->stream);
-        c->launches += k;
-        if (tm) tm->end(c, k);
+        if (!c->fuse_small) {
+                if (tm) tm->begin(c, BLK_PH_SMALL);
+                k = launch_small(g, c->m, c->sums, c->mats, c->state, 0, c->stream);
+                c->launches += k;
+                if (tm) tm->end(c, k);
+        }
         if (tm) tm->begin(c, BLK_PH_ORTHO);
         k = launch_ortho(g, c->m, lrows, vloc, c->Av, c->p, vloc, c->p, c->mats, c->state, 0, c->stream);
         c->launches += k;
@@ -325,7 +374,7 @@ int build_graph(blk_ctx *c)
         return 0;
 }
 
-int kernels_per_iteration(const blk_ctx *) { return 7; }
+int kernels_per_iteration(const blk_ctx *c) { return c->fuse_small ? 6 : 7; }
 
 }  // namespace
 
@@ -386,7 +435,7 @@ int blk_destroy(blk_ctx *c)
         free_operator(&c->S1);
         free_operator(&c->S2);
         cudaFree(c->v); cudaFree(c->tmp); cudaFree(c->Av); cudaFree(c->p);
-        cudaFree(c->mats); cudaFree(c->sums); cudaFree(c->state);
+        cudaFree(c->mats); cudaFree(c->sums); cudaFree(c->state); cudaFree(c->dots_counter);
         if (c->h_state) cudaFreeHost(c->h_state);
         if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
         delete c;
@@ -523,7 +572,7 @@ int blk_create(blk_ctx **out, const blk_params *prm)
 
         // ---- vector blocks and the small working set
         int64_t ln = c->n1() - c->n0();
-        size_t bv = sizeof(u32) * (size_t)c->N * np, bt = sizeof(u32) * (size_t)c->Mc * np;
+        size_t bv = sizeof(u32) * (size_t)gather_cap(c->n_off) * np, bt = sizeof(u32) * (size_t)gather_cap(c->m_off) * np;
         size_t bl = sizeof(u32) * (size_t)(ln > 0 ? ln : 1) * np;
         CUX(cudaMalloc(&c->v, bv)); CUX(cudaMalloc(&c->tmp, bt));
         CUX(cudaMalloc(&c->Av, bl)); CUX(cudaMalloc(&c->p, bl));
@@ -531,11 +580,17 @@ int blk_create(blk_ctx **out, const blk_params *prm)
         CUX(cudaMemsetAsync(c->Av, 0, bl, c->stream)); CUX(cudaMemsetAsync(c->p, 0, bl, c->stream));
         c->block_bytes = bv + bt + 2 * bl;
         c->dots_blocks = dots_num_blocks(ln, np);
-        CUX(cudaMalloc(&c->mats, sizeof(u32) * (size_t)MAT_COUNT * np * np));
+        CUX(cudaMalloc(&c->mats, sizeof(u32) * mats_words(np)));
         CUX(cudaMalloc(&c->sums, sizeof(u64) * (size_t)2 * np * np));
         CUX(cudaMalloc(&c->state, sizeof(DevSmall)));
+        CUX(cudaMalloc(&c->dots_counter, sizeof(unsigned)));
+        CUX(cudaMemsetAsync(c->dots_counter, 0, sizeof(unsigned), c->stream));
+        {
+                const char *e = getenv("BLK_FUSE_SMALL");
+                c->fuse_small = world == 1 && np <= 32 && !(e && e[0] == '0');
+        }
         CUX(cudaMallocHost(&c->h_state, sizeof(DevSmall)));
-        CUX(cudaMemsetAsync(c->mats, 0, sizeof(u32) * (size_t)MAT_COUNT * np * np, c->stream));
+        CUX(cudaMemsetAsync(c->mats, 0, sizeof(u32) * mats_words(np), c->stream));
         CUX(cudaMemsetAsync(c->sums, 0, sizeof(u64) * (size_t)2 * np * np, c->stream));
         memset(c->h_state, 0, sizeof(DevSmall));
         c->h_state->halt = 1;
@@ -553,6 +608,8 @@ int blk_create(blk_ctx **out, const blk_params *prm)
                         blk_destroy(c);
                         return 1;
                 }
+                const char *e = getenv("BLK_ALLGATHER");
+                if (!(e && e[0] == 'b')) c->nccl_allgather = g_nccl.AllGather;     // BLK_ALLGATHER=bcast forces broadcasts
         }
 #undef CUX
         *out = c;
@@ -677,7 +734,7 @@ int blk_get_state(blk_ctx *c, uint32_t *v, uint32_t *tmp, uint32_t *Av, uint32_t
                         if (download_rows(c, dst, src, N)) return 1;
                 } else {
                         u32 *full = nullptr;
-                        CU(cudaMalloc(&full, sizeof(u32) * (size_t)N * np));
+                        CU(cudaMalloc(&full, sizeof(u32) * (size_t)gather_cap(c->n_off) * np));
                         int64_t ln = c->n1() - c->n0();
                         CU(cudaMemcpyAsync(full + (size_t)c->n0() * np, src, sizeof(u32) * (size_t)ln * np,
                                            cudaMemcpyDeviceToDevice, c->stream));
@@ -729,7 +786,7 @@ int blk_spmv(blk_ctx *c, uint32_t *y, const uint32_t *x, int32_t transpose)
         int64_t out_rows = s1 ? c->Mc : c->N, in_rows = s1 ? c->N : c->Mc;
         u32 *dx = nullptr, *dy = nullptr;
         CU(cudaMalloc(&dx, sizeof(u32) * (size_t)in_rows * np));
-        CU(cudaMalloc(&dy, sizeof(u32) * (size_t)out_rows * np));
+        CU(cudaMalloc(&dy, sizeof(u32) * (size_t)gather_cap(off) * np));
         int rc = upload_rows(c, dx, x, in_rows);
         if (!rc) {
                 // poison the output: every row must be written by the kernels
@@ -758,11 +815,11 @@ int blk_block_dot_products(blk_ctx *c, uint32_t *vtAv, uint32_t *vtAAv, int64_t 
         CU(cudaMalloc(&dv, sizeof(u32) * (size_t)rows * np));
         CU(cudaMalloc(&da, sizeof(u32) * (size_t)rows * np));
         CU(cudaMalloc(&sums, sizeof(u64) * (size_t)2 * np * np));
-        CU(cudaMalloc(&mats, sizeof(u32) * (size_t)MAT_COUNT * np * np));
+        CU(cudaMalloc(&mats, sizeof(u32) * mats_words(np)));
         CU(cudaMemsetAsync(sums, 0, sizeof(u64) * (size_t)2 * np * np, c->stream));
         int rc = upload_rows(c, dv, v, N) || upload_rows(c, da, Av, N);
         if (!rc) {
-                c->launches += launch_dots(c->geo, c->m, N, dv, da, sums, nblocks, nullptr, c->stream);
+                c->launches += launch_dots(c->geo, c->m, N, dv, da, sums, nblocks, nullptr, SmallFuse(), c->stream);
                 c->launches += launch_small(c->geo, c->m, sums, mats, c->state, 1, c->stream);
                 std::vector<u32> h((size_t)2 * np * np);
                 cudaMemcpyAsync(h.data(), mats, sizeof(u32) * h.size(), cudaMemcpyDeviceToHost, c->stream);
@@ -794,7 +851,7 @@ int blk_semi_inverse(blk_ctx *c, const uint32_t *M_, uint32_t *winv, uint32_t *d
         put_small(h, MAT_VTAV, M_, n, np);
         u32 *mats = nullptr;
         DevSmall *st = nullptr;
-        CU(cudaMalloc(&mats, sizeof(u32) * h.size()));
+        CU(cudaMalloc(&mats, sizeof(u32) * mats_words(np)));
         CU(cudaMalloc(&st, sizeof(DevSmall)));
         CU(cudaMemsetAsync(st, 0, sizeof(DevSmall), c->stream));
         CU(cudaMemcpyAsync(mats, h.data(), sizeof(u32) * h.size(), cudaMemcpyHostToDevice, c->stream));
@@ -826,7 +883,7 @@ int blk_orthogonalize(blk_ctx *c, const uint32_t *v, uint32_t *tmp, uint32_t *p,
         for (int j = 0; j < n; j++) h[(size_t)MAT_D * np * np + j] = d[j];
         int64_t rows = N > 0 ? N : 1;
         u32 *mats = nullptr, *dv = nullptr, *da = nullptr, *dp = nullptr, *dvo = nullptr;
-        CU(cudaMalloc(&mats, sizeof(u32) * h.size()));
+        CU(cudaMalloc(&mats, sizeof(u32) * mats_words(np)));
         CU(cudaMalloc(&dv, sizeof(u32) * (size_t)rows * np));
         CU(cudaMalloc(&dvo, sizeof(u32) * (size_t)rows * np));
         CU(cudaMalloc(&da, sizeof(u32) * (size_t)rows * np));

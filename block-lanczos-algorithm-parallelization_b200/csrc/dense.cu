@@ -10,6 +10,7 @@
 // lazy fold of modp.cuh and reduce once per output.  Blocks are stored with leading dimension
 // n_pad (power of two >= n, extra columns are zero and stay zero through every phase).
 #include "blk_internal.cuh"
+#include "small_body.cuh"
 
 namespace {
 
@@ -42,15 +43,19 @@ template <int V> __device__ __forceinline__ void stv(u32 *p, const u32 (&o)[V])
 // ------------------------------------------------------------------------------------------
 template <int NP, int FOLD>
 __global__ void __launch_bounds__(DOTS_TB)
-k_dots(int64_t rows, const u32 *__restrict__ v, const u32 *__restrict__ Av, unsigned long long *__restrict__ sums,
-       ModP m, const DevSmall *__restrict__ state)
+k_dots(int64_t rows, const u32 *__restrict__ v, const u32 *__restrict__ Av, unsigned long long *sums,
+       ModP m, const DevSmall *state, SmallFuse fuse)
 {
         constexpr int TI = NP < 4 ? NP : 4;
         constexpr int PER = NP / TI;          // tiles per dimension
         constexpr int T = PER * PER;          // threads per team
         constexpr int TEAMS = DOTS_TB / T;
         constexpr int FE = FOLD ? FOLD : 64;  // rows between folds
-        if (state && state->halt) return;
+        if (state && state->halt) {
+                // a halted iteration must not re-run orthogonalize (k_small would have cleared the flag)
+                if (fuse.counter && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) fuse.state->do_ortho = 0;
+                return;
+        }
 
         const int tid = threadIdx.x;
         const int team = tid / T, tt = tid % T;
@@ -86,204 +91,64 @@ k_dots(int64_t rows, const u32 *__restrict__ v, const u32 *__restrict__ Av, unsi
 
         // block result -> global u64 sums (integer addition: order-free, hence deterministic).
         // Every addend is a canonical residue < 2^31, so 2^33 blocks could not overflow.
+        // Teams inside a warp are combined with shuffles first (mod-p adds on u32).
+        constexpr int TPW = T < 32 ? 32 / T : 1;       // teams per warp
+        u32 r1[TI][TI], r2[TI][TI];
+#pragma unroll
+        for (int a = 0; a < TI; a++)
+#pragma unroll
+                for (int b = 0; b < TI; b++) {
+                        u32 x = mp_reduce(a1[a][b], m), y = mp_reduce(a2[a][b], m);
+#pragma unroll
+                        for (int off = T; off < T * TPW; off <<= 1) {
+                                x = mp_add(x, __shfl_xor_sync(0xffffffffu, x, off), m);
+                                y = mp_add(y, __shfl_xor_sync(0xffffffffu, y, off), m);
+                        }
+                        r1[a][b] = x; r2[a][b] = y;
+                }
+        const bool writer = T >= 32 || (tid & 31) < T;  // one team per warp carries the warp's result
         if (TEAMS == 1) {
 #pragma unroll
                 for (int a = 0; a < TI; a++)
 #pragma unroll
                         for (int b = 0; b < TI; b++) {
-                                atomicAdd(&sums[(i0 + a) * NP + j0 + b], (unsigned long long)mp_reduce(a1[a][b], m));
-                                atomicAdd(&sums[NP * NP + (i0 + a) * NP + j0 + b], (unsigned long long)mp_reduce(a2[a][b], m));
+                                atomicAdd(&sums[(i0 + a) * NP + j0 + b], (unsigned long long)r1[a][b]);
+                                atomicAdd(&sums[NP * NP + (i0 + a) * NP + j0 + b], (unsigned long long)r2[a][b]);
                         }
         } else {
                 __shared__ unsigned long long acc[TEAMS == 1 ? 1 : 2 * NP * NP];
                 for (int e = tid; e < 2 * NP * NP; e += DOTS_TB) acc[e] = 0;
                 __syncthreads();
+                if (writer) {
 #pragma unroll
-                for (int a = 0; a < TI; a++)
+                        for (int a = 0; a < TI; a++)
 #pragma unroll
-                        for (int b = 0; b < TI; b++) {
-                                atomicAdd(&acc[(i0 + a) * NP + j0 + b], (unsigned long long)mp_reduce(a1[a][b], m));
-                                atomicAdd(&acc[NP * NP + (i0 + a) * NP + j0 + b], (unsigned long long)mp_reduce(a2[a][b], m));
-                        }
+                                for (int b = 0; b < TI; b++) {
+                                        atomicAdd(&acc[(i0 + a) * NP + j0 + b], (unsigned long long)r1[a][b]);
+                                        atomicAdd(&acc[NP * NP + (i0 + a) * NP + j0 + b], (unsigned long long)r2[a][b]);
+                                }
+                }
                 __syncthreads();
                 for (int e = tid; e < 2 * NP * NP; e += DOTS_TB)
                         atomicAdd(&sums[e], (unsigned long long)mp_reduce(acc[e], m));
         }
+        if (fuse.counter && last_block_done(fuse.counter, gridDim.x)) {
+                extern __shared__ u32 sm_fused[];
+                small_body(fuse.n, NP, sums, fuse.mats, fuse.state, 0, m, sm_fused);
+        }
 }
 
 // ------------------------------------------------------------------------------------------
-// small: one block.  Working matrices use the true n as leading dimension in shared memory.
+// small: one block (see small_body.cuh)
 // ------------------------------------------------------------------------------------------
 constexpr int SMALL_TB = 256;
 
-struct GjBuf { u32 *M, *W, *scal; };
-
-// One Gauss-Jordan sweep of semi_inverse (sequential/lanczos_modp.c:351-382 and :393-436): for
-// each column j the FIRST row i >= j with a non-zero entry is the pivot; the reference scales that
-// row by the inverse of the pivot, swaps it into row j and clears column j in every other row.
-//
-// Done here fraction-free so that no modular inverse sits on the serial path: row i of the
-// working matrices is kept as scal[i] times the reference's row (scal[i] != 0), the update is
-//      row_i <- pv * row_i - row_i[j] * row_piv        scal[i] <- scal[i] * pv     (i != j)
-//      row_j <- row_piv                                scal[j] <- pv
-// Zero patterns -- and therefore every pivot decision -- are identical to the reference's, and
-// dividing row i by scal[i] at the end (n independent inverses, one per thread) gives exactly
-// the reference's W.  Double buffered in shared memory: one barrier per pivot column.
-// Returns the number of pivots; d[j] = 1 on pivot columns; *cur = buffer holding the result.
-__device__ int gj_sweep(GjBuf *buf, int *cur, bool carry_w, u32 *d, int n, const ModP &m)
-{
-        const int tid = threadIdx.x;
-        int found = 0, s = *cur;
-        for (int j = 0; j < n; j++) {
-                const u32 *Ms = buf[s].M, *Ws = buf[s].W, *ss = buf[s].scal;
-                u32 *Md = buf[s ^ 1].M, *Wd = buf[s ^ 1].W, *sd = buf[s ^ 1].scal;
-                int piv = -1;
-                for (int i = j; i < n; i++)
-                        if (Ms[i * n + j] != 0) { piv = i; break; }       // same answer in every thread
-                if (tid == 0) d[j] = piv >= 0;
-                if (piv < 0) continue;
-                found++;
-                const u32 pv = Ms[piv * n + j];
-                for (int e = tid; e < n * n; e += SMALL_TB) {
-                        const int i = e / n, k = e - i * n;
-                        if (i == j) {
-                                Md[e] = Ms[piv * n + k];
-                                if (carry_w) Wd[e] = Ws[piv * n + k];
-                        } else {
-                                const int r = (i == piv) ? j : i;           // row i after the swap
-                                const u32 f = mp_neg(Ms[r * n + j], m);
-                                Md[e] = mp_reduce((u64)pv * Ms[r * n + k] + (u64)f * Ms[piv * n + k], m);
-                                if (carry_w) Wd[e] = mp_reduce((u64)pv * Ws[r * n + k] + (u64)f * Ws[piv * n + k], m);
-                        }
-                }
-                if (carry_w)
-                        for (int i = tid; i < n; i += SMALL_TB) {
-                                const int r = (i == piv) ? j : i;
-                                sd[i] = (i == j) ? pv : mp_mul(ss[r], pv, m);
-                        }
-                __syncthreads();
-                s ^= 1;
-        }
-        *cur = s;
-        return found;
-}
-
-// mode 0: full step; 1: reduce dots only; 2: semi_inverse of mats[VTAV]; 3: coefficients only
 __global__ void __launch_bounds__(SMALL_TB)
 k_small(int n, int np, unsigned long long *__restrict__ sums, u32 *__restrict__ mats,
         DevSmall *__restrict__ state, int mode, ModP m)
 {
-        extern __shared__ u32 sm[];
-        const int tid = threadIdx.x;
-        const int nn = n * n, npp = np * np;
-        u32 *A = sm;               // vtAv   (n x n)
-        u32 *B = A + nn;           // vtAAv
-        GjBuf buf[2];
-        buf[0].M = B + nn;   buf[0].W = buf[0].M + nn;
-        buf[1].M = buf[0].W + nn; buf[1].W = buf[1].M + nn;
-        buf[0].scal = buf[1].W + nn; buf[1].scal = buf[0].scal + n;
-        u32 *d = buf[1].scal + n;  // n
-        u32 *d1 = d + n;           // n (phase-1 pivots)
-
-        if (mode == 0 && state->halt) {
-                if (tid == 0) state->do_ortho = 0;
-                return;
-        }
-
-        // ---- gather the dot products (and clear the accumulators for the next iteration)
-        if (mode <= 1) {
-                for (int e = tid; e < 2 * npp; e += SMALL_TB) {
-                        int which = e / npp, r = e - which * npp;
-                        int i = r / np, j = r - i * np;
-                        u32 val = mp_reduce(sums[e], m);
-                        sums[e] = 0;
-                        if (i < n && j < n) (which ? B : A)[i * n + j] = val;
-                        mats[(which ? MAT_VTAAV : MAT_VTAV) * npp + r] = val;
-                }
-                if (mode == 1) return;
-        } else {
-                for (int e = tid; e < nn; e += SMALL_TB) {
-                        int i = e / n, j = e - i * n;
-                        A[e] = mats[MAT_VTAV * npp + i * np + j];
-                        B[e] = mats[MAT_VTAAV * npp + i * np + j];
-                }
-        }
-        __syncthreads();
-
-        int npiv = 0;
-        u32 *W = buf[0].W;
-        if (mode == 0 || mode == 2) {
-                // ---- semi_inverse, phase 1: which columns carry a pivot
-                int cur = 0;
-                for (int e = tid; e < nn; e += SMALL_TB) buf[0].M[e] = A[e];
-                __syncthreads();
-                gj_sweep(buf, &cur, false, d1, n, m);
-                __syncthreads();
-                // ---- phase 2 on the d x d restriction, carrying winv along
-                for (int e = tid; e < nn; e += SMALL_TB) {
-                        int i = e / n, j = e - i * n;
-                        bool keep = d1[i] && d1[j];
-                        buf[cur].M[e] = keep ? A[e] : 0u;
-                        buf[cur].W[e] = (i == j && d1[i]) ? 1u : 0u;
-                }
-                for (int i = tid; i < n; i += SMALL_TB) buf[cur].scal[i] = 1u;
-                __syncthreads();
-                npiv = gj_sweep(buf, &cur, true, d, n, m);
-                __syncthreads();
-                // undo the row scalings: n independent inverses, one per thread
-                for (int i = tid; i < n; i += SMALL_TB) buf[cur].scal[i] = mp_inv(buf[cur].scal[i], m);
-                __syncthreads();
-                W = buf[cur].W;
-                for (int e = tid; e < nn; e += SMALL_TB) W[e] = mp_mul(W[e], buf[cur].scal[e / n], m);
-                __syncthreads();
-                for (int e = tid; e < npp; e += SMALL_TB) {
-                        int i = e / np, j = e - i * np;
-                        mats[MAT_WINV * npp + e] = (i < n && j < n) ? W[i * n + j] : 0u;
-                }
-                for (int j = tid; j < np; j += SMALL_TB) mats[MAT_D * npp + j] = j < n ? d[j] : 0u;
-                if (tid == 0) state->npiv = npiv;
-                if (mode == 2) return;
-        } else {
-                for (int e = tid; e < nn; e += SMALL_TB) {
-                        int i = e / n, j = e - i * n;
-                        W[e] = mats[MAT_WINV * npp + i * np + j];
-                }
-                for (int j = tid; j < n; j += SMALL_TB) d[j] = mats[MAT_D * npp + j];
-                __syncthreads();
-                npiv = 1;
-        }
-
-        // ---- coefficients of orthogonalize (sequential/lanczos_modp.c:460-475)
-        //   c     = -(winv * spliced), spliced[:,j] = d[j] ? vtAAv[:,j] : vtAv[:,j]
-        //   vtAvd = d[j] ? -vtAv[:,j] : 0
-        // (the reference stores p - x, which may equal p; canonical here, same value mod p)
-        for (int e = tid; e < npp; e += SMALL_TB) {
-                int i = e / np, j = e - i * np;
-                u32 cval = 0, dval = 0;
-                if (i < n && j < n) {
-                        const u32 *S = d[j] ? B : A;
-                        u64 s = 0;
-                        for (int k = 0; k < n; k++) {
-                                s += (u64)W[i * n + k] * S[k * n + j];
-                                mp_fold(s, m);
-                        }
-                        cval = mp_neg(mp_reduce(s, m), m);
-                        dval = d[j] ? mp_neg(A[i * n + j], m) : 0u;
-                }
-                mats[MAT_C * npp + e] = cval;
-                mats[MAT_VTAVD * npp + e] = dval;
-        }
-
-        if (mode == 0 && tid == 0) {
-                if (npiv == 0) {
-                        state->stopped = 1; state->halt = 1; state->do_ortho = 0;
-                } else {
-                        int it = state->iters + 1;
-                        state->iters = it;
-                        state->do_ortho = 1;
-                        if (state->limit > 0 && it >= state->limit) state->halt = 1;
-                }
-        }
+        extern __shared__ u32 sm_small[];
+        small_body(n, np, sums, mats, state, mode, m, sm_small);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -403,12 +268,13 @@ __global__ void k_unpad_rows(const u32 *__restrict__ src, u32 *__restrict__ dst,
 
 template <int NP>
 int dots_fold(const ModP &m, int64_t rows, const u32 *v, const u32 *Av, u64 *sums, int nblocks,
-              const DevSmall *state, cudaStream_t st)
+              const DevSmall *state, const SmallFuse &fuse, cudaStream_t st)
 {
+        size_t smem = fuse.counter ? sizeof(u32) * small_smem_words(fuse.n) : 0;
         switch (m.fold_every) {
-        case 0: k_dots<NP, 0><<<nblocks, DOTS_TB, 0, st>>>(rows, v, Av, (unsigned long long *)sums, m, state); break;
-        case 8: k_dots<NP, 8><<<nblocks, DOTS_TB, 0, st>>>(rows, v, Av, (unsigned long long *)sums, m, state); break;
-        default: k_dots<NP, 2><<<nblocks, DOTS_TB, 0, st>>>(rows, v, Av, (unsigned long long *)sums, m, state); break;
+        case 0: k_dots<NP, 0><<<nblocks, DOTS_TB, smem, st>>>(rows, v, Av, (unsigned long long *)sums, m, state, fuse); break;
+        case 8: k_dots<NP, 8><<<nblocks, DOTS_TB, smem, st>>>(rows, v, Av, (unsigned long long *)sums, m, state, fuse); break;
+        default: k_dots<NP, 2><<<nblocks, DOTS_TB, smem, st>>>(rows, v, Av, (unsigned long long *)sums, m, state, fuse); break;
         }
         return 1;
 }
@@ -447,23 +313,24 @@ int dots_num_blocks(int64_t rows, int np)
         int ti = np < 4 ? np : 4;
         int team = (np / ti) * (np / ti);
         int teams = DOTS_TB / team;
-        int64_t want = (rows + (int64_t)teams * 16 - 1) / ((int64_t)teams * 16);   // >= 16 rows per team
+        int64_t want = (rows + (int64_t)teams * 4 - 1) / ((int64_t)teams * 4);     // >= 4 rows per team
         if (want < 1) want = 1;
         if (want > 148 * 4) want = 148 * 4;
         return (int)want;
 }
 
 int launch_dots(const Geometry &geo, const ModP &m, int64_t rows, const u32 *v, const u32 *Av,
-                u64 *sums, int nblocks, const DevSmall *state, cudaStream_t st)
+                u64 *sums, int nblocks, const DevSmall *state, const SmallFuse &fuse, cudaStream_t st)
 {
+        if (dense_mma_supported(geo.np)) return launch_dots_mma(geo.np, m, rows, v, Av, sums, state, fuse, st);
         switch (geo.np) {
-        case 1: return dots_fold<1>(m, rows, v, Av, sums, nblocks, state, st);
-        case 2: return dots_fold<2>(m, rows, v, Av, sums, nblocks, state, st);
-        case 4: return dots_fold<4>(m, rows, v, Av, sums, nblocks, state, st);
-        case 8: return dots_fold<8>(m, rows, v, Av, sums, nblocks, state, st);
-        case 16: return dots_fold<16>(m, rows, v, Av, sums, nblocks, state, st);
-        case 32: return dots_fold<32>(m, rows, v, Av, sums, nblocks, state, st);
-        case 64: return dots_fold<64>(m, rows, v, Av, sums, nblocks, state, st);
+        case 1: return dots_fold<1>(m, rows, v, Av, sums, nblocks, state, fuse, st);
+        case 2: return dots_fold<2>(m, rows, v, Av, sums, nblocks, state, fuse, st);
+        case 4: return dots_fold<4>(m, rows, v, Av, sums, nblocks, state, fuse, st);
+        case 8: return dots_fold<8>(m, rows, v, Av, sums, nblocks, state, fuse, st);
+        case 16: return dots_fold<16>(m, rows, v, Av, sums, nblocks, state, fuse, st);
+        case 32: return dots_fold<32>(m, rows, v, Av, sums, nblocks, state, fuse, st);
+        case 64: return dots_fold<64>(m, rows, v, Av, sums, nblocks, state, fuse, st);
         }
         return -1;
 }
@@ -471,7 +338,7 @@ int launch_dots(const Geometry &geo, const ModP &m, int64_t rows, const u32 *v, 
 int launch_small(const Geometry &geo, const ModP &m, u64 *sums, u32 *mats, DevSmall *state, int mode,
                  cudaStream_t st)
 {
-        size_t smem = sizeof(u32) * (6 * (size_t)geo.n * geo.n + 4 * geo.n + 8);
+        size_t smem = sizeof(u32) * small_smem_words(geo.n);
         k_small<<<1, SMALL_TB, smem, st>>>(geo.n, geo.np, (unsigned long long *)sums, mats, state, mode, m);
         return 1;
 }
@@ -479,6 +346,8 @@ int launch_small(const Geometry &geo, const ModP &m, u64 *sums, u32 *mats, DevSm
 int launch_ortho(const Geometry &geo, const ModP &m, int64_t rows, u32 *v, const u32 *Av, u32 *p,
                  u32 *v_out, u32 *p_out, const u32 *mats, const DevSmall *state, int force, cudaStream_t st)
 {
+        if (rows >= 0 && dense_mma_supported(geo.np))
+                return launch_ortho_mma(geo.np, m, rows, v, Av, p, v_out, p_out, mats, state, force, st);
         switch (geo.np) {
         case 1: return ortho_fold<1, 1>(rows, v, Av, p, v_out, p_out, mats, m, state, force, st);
         case 2: return ortho_fold<2, 2>(rows, v, Av, p, v_out, p_out, mats, m, state, force, st);
@@ -495,6 +364,7 @@ void dense_prepare(const Geometry &geo, const ModP &m)
 {
         cudaFuncSetAttribute(k_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
         launch_ortho(geo, m, -1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr);
+        dense_mma_prepare(geo.np);
 }
 
 int launch_pad_rows(const u32 *src, u32 *dst, int64_t rows, int n, int np, cudaStream_t st)
