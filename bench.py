@@ -316,9 +316,17 @@ def main():
         tj = json.load(open(tpath))
         if tj.get("workload") == a.workload and tj.get("n_gpus", 1) == world:
             traffic = tj.get("dram_bytes_per_launch")
+    dram = None
+    if traffic:
+        # both products move the same bytes to within 1%; `traffic` is one launch
+        dram = {"bytes_per_launch": traffic, "achieved": 2 * traffic / (t_spmv * 1e-3) / 1e9,
+                "frac": 2 * traffic / (t_spmv * 1e-3) / 1e9 / peak,
+                "note": "ncu dram__bytes_read+write of one k_spmv launch (profiles/r01_spmv_cfg4_ncu_summary.txt): "
+                        "every L2 miss fills a 128 B line, so a 64 B x-row gather costs 128 B of HBM traffic "
+                        "(profiles/r01_gather_granularity.txt)"}
     roofline = {"kernel": "k_spmv (both products of one iteration)", "bound": "hbm", "achieved": achieved,
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                "algorithmic_bytes_per_iteration": b1 + b2, "traffic": traffic,
+                "algorithmic_bytes_per_iteration": b1 + b2, "traffic": traffic, "dram": dram,
                 "gather_model": {"bytes_per_iteration": g1 + g2, "achieved": achieved_g, "frac": achieved_g / peak,
                                  "note": "x block (3.2 GB) >> L2: every non-zero gathers its own 4n-byte x row"},
                 "ms_per_launch_pair": t_spmv, "frac_of_nominal_8TBs": achieved / 8000.0}

@@ -37,6 +37,7 @@ struct SpOp {
         u32 *span = nullptr;       // [ntiles]    number of following tiles that finish that row (0: none)
         u32 *whead = nullptr;      // [ntiles*n_pad] scratch: the tile's contribution to a row opened earlier
         size_t bytes = 0;
+        u32 hot_cols = 0;          // > 0: x rows [0, hot_cols) are gathered with L2 evict_last, the rest evict_first
 };
 
 // n x n working set of one iteration, resident on the device.  All matrices are stored with
@@ -74,8 +75,11 @@ static inline Geometry make_geometry(int n)
 // layout_build.cu
 std::string build_operator(SpOp *op, const Geometry &geo, int chunk_len, int64_t rows, int64_t cols,
                            int64_t row_lo, int64_t nnz, const int32_t *d_row, const int32_t *d_col,
-                           const u32 *d_val, u32 prime, cudaStream_t st);
+                           const u32 *d_val, u32 prime, const u32 *row_map, const u32 *col_map, cudaStream_t st);
 void free_operator(SpOp *op);
+// old->new / new->old labels of one dimension sorted by decreasing number of entries
+std::string degree_sort_maps(int64_t nnz, const int32_t *d_idx, int64_t dim, u32 **old2new, u32 **new2old,
+                             cudaStream_t st);
 
 // spmv.cu
 int launch_spmv(const SpOp &op, const Geometry &geo, const ModP &m, const u32 *x, u32 *y,
@@ -121,5 +125,6 @@ int launch_dots_mma(int np, const ModP &m, int64_t rows, const u32 *v, const u32
 // per-device one-time kernel attributes (call with the device current, outside stream capture)
 void dense_prepare(const Geometry &geo, const ModP &m);
 // n <-> n_pad repacking of row-major blocks (rows x n  <->  rows x np)
-int launch_pad_rows(const u32 *src, u32 *dst, int64_t rows, int n, int np, cudaStream_t st);
-int launch_unpad_rows(const u32 *src, u32 *dst, int64_t rows, int n, int np, cudaStream_t st);
+// `map` (nullable) relabels rows: pad: dst[r] = src[map[r]]; unpad: dst[r] = src[map[r]]
+int launch_pad_rows(const u32 *src, u32 *dst, int64_t rows, int n, int np, const u32 *map, cudaStream_t st);
+int launch_unpad_rows(const u32 *src, u32 *dst, int64_t rows, int n, int np, const u32 *map, cudaStream_t st);

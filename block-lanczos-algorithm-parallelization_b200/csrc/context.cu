@@ -98,6 +98,8 @@ struct blk_ctx {
         u32 *Av = nullptr, *p = nullptr;        // local rows [n0,n1) * np
         u32 *mats = nullptr;
         u64 *sums = nullptr;                   // 2*np*np dot-product accumulators (zero between iterations)
+        u32 *n_old2new = nullptr, *n_new2old = nullptr;   // degree-sorted relabelling of the N dimension (or null)
+        int64_t hot_rows = 0;
         unsigned *dots_counter = nullptr;      // last-block-done ticket of the fused dots + small kernel
         bool fuse_small = false;
         DevSmall *state = nullptr, *h_state = nullptr;
@@ -317,11 +319,12 @@ int pull_state(blk_ctx *c)
 }
 
 // host block (rows x n, row-major) -> device block with leading dimension np
-int upload_rows(blk_ctx *c, u32 *dst, const u32 *src_host, int64_t rows)
+// `map` (device, nullable): dst row r comes from host row map[r]
+int upload_rows(blk_ctx *c, u32 *dst, const u32 *src_host, int64_t rows, const u32 *map = nullptr)
 {
         const int n = c->geo.n, np = c->geo.np;
         if (rows == 0) return 0;
-        if (n == np) {
+        if (n == np && !map) {
                 CU(cudaMemcpyAsync(dst, src_host, sizeof(u32) * (size_t)rows * n, cudaMemcpyHostToDevice, c->stream));
                 CU(cudaStreamSynchronize(c->stream));
                 return 0;
@@ -329,23 +332,24 @@ int upload_rows(blk_ctx *c, u32 *dst, const u32 *src_host, int64_t rows)
         u32 *stage = nullptr;
         CU(cudaMalloc(&stage, sizeof(u32) * (size_t)rows * n));
         CU(cudaMemcpyAsync(stage, src_host, sizeof(u32) * (size_t)rows * n, cudaMemcpyHostToDevice, c->stream));
-        c->launches += launch_pad_rows(stage, dst, rows, n, np, c->stream);
+        c->launches += launch_pad_rows(stage, dst, rows, n, np, map, c->stream);
         CU(cudaStreamSynchronize(c->stream));
         cudaFree(stage);
         return 0;
 }
-int download_rows(blk_ctx *c, u32 *dst_host, const u32 *src, int64_t rows)
+// `map` (device, nullable): host row r comes from device row map[r]
+int download_rows(blk_ctx *c, u32 *dst_host, const u32 *src, int64_t rows, const u32 *map = nullptr)
 {
         const int n = c->geo.n, np = c->geo.np;
         if (rows == 0) return 0;
-        if (n == np) {
+        if (n == np && !map) {
                 CU(cudaMemcpyAsync(dst_host, src, sizeof(u32) * (size_t)rows * n, cudaMemcpyDeviceToHost, c->stream));
                 CU(cudaStreamSynchronize(c->stream));
                 return 0;
         }
         u32 *stage = nullptr;
         CU(cudaMalloc(&stage, sizeof(u32) * (size_t)rows * n));
-        c->launches += launch_unpad_rows(src, stage, rows, n, np, c->stream);
+        c->launches += launch_unpad_rows(src, stage, rows, n, np, map, c->stream);
         CU(cudaMemcpyAsync(dst_host, stage, sizeof(u32) * (size_t)rows * n, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
         cudaFree(stage);
@@ -436,6 +440,7 @@ int blk_destroy(blk_ctx *c)
         free_operator(&c->S2);
         cudaFree(c->v); cudaFree(c->tmp); cudaFree(c->Av); cudaFree(c->p);
         cudaFree(c->mats); cudaFree(c->sums); cudaFree(c->state); cudaFree(c->dots_counter);
+        cudaFree(c->n_old2new); cudaFree(c->n_new2old);
         if (c->h_state) cudaFreeHost(c->h_state);
         if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
         delete c;
@@ -525,6 +530,27 @@ int blk_create(blk_ctx **out, const blk_params *prm)
                 }
         }
 
+        // ---- degree-sorted labels for the N dimension + L2-resident hot prefix (single GPU)
+        {
+                const char *e = getenv("BLK_HOT"), *emin = getenv("BLK_HOT_MIN_BYTES"), *eb = getenv("BLK_HOT_BYTES");
+                cudaDeviceProp prop;
+                CUX(cudaGetDeviceProperties(&prop, c->device));
+                long long min_bytes = emin ? atoll(emin) : 96ll << 20;
+                long long hot_bytes = eb ? atoll(eb) : 24ll << 20;
+                bool on = world == 1 && !(e && e[0] == '0') && np >= 4 && nnz > 0 &&
+                          (long long)c->N * np * 4 > min_bytes && hot_bytes > 0;
+                if (on) {
+                        std::string err = degree_sort_maps(nnz, idxN, c->N, &c->n_old2new, &c->n_new2old, c->stream);
+                        if (!err.empty()) { free_coo(); fail(err); blk_destroy(c); return 1; }
+                        c->hot_rows = std::min<int64_t>(c->N, hot_bytes / (4 * np));
+                        // B200's L2 is two halves (one per die) and lines gathered by SMs of both dies live
+                        // in both, so the set-aside has to hold the hot prefix twice
+                        const char *ep = getenv("BLK_L2_PERSIST");
+                        long long persist = ep ? atoll(ep) : std::min<long long>(prop.persistingL2CacheMaxSize, 2 * hot_bytes);
+                        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)persist);
+                }
+        }
+
         // ---- the two operators.  S1: rows = my block of the Mc dimension, columns = N dimension;
         //      S2: rows = my block of the N dimension, columns = Mc dimension.
         for (int which = 0; which < 2; which++) {
@@ -534,7 +560,9 @@ int blk_create(blk_ctx **out, const blk_params *prm)
                 int64_t cols = which ? c->Mc : c->N;
                 std::string err;
                 if (world == 1) {
-                        err = build_operator(op, c->geo, prm->chunk_len, hi - lo, cols, lo, nnz, rk, ck, dx, m.p, c->stream);
+                        err = build_operator(op, c->geo, prm->chunk_len, hi - lo, cols, lo, nnz, rk, ck, dx, m.p,
+                                             which ? c->n_old2new : nullptr, which ? nullptr : c->n_old2new, c->stream);
+                        if (!which) op->hot_cols = (u32)c->hot_rows;
                 } else {
                         int32_t *sr = nullptr, *sc = nullptr; u32 *sx = nullptr;
                         unsigned long long *cnt = nullptr, hcnt = 0;
@@ -562,7 +590,7 @@ int blk_create(blk_ctx **out, const blk_params *prm)
                         CUX(cudaStreamSynchronize(c->stream));
                         cudaFree(cnt);
                         if ((int64_t)hcnt != sel) err = "shard selection count mismatch";
-                        else err = build_operator(op, c->geo, prm->chunk_len, hi - lo, cols, lo, sel, sr, sc, sx, m.p, c->stream);
+                        else err = build_operator(op, c->geo, prm->chunk_len, hi - lo, cols, lo, sel, sr, sc, sx, m.p, nullptr, nullptr, c->stream);
                         cudaFree(sr); cudaFree(sc); cudaFree(sx);
                 }
                 if (!err.empty()) { free_coo(); fail(err); blk_destroy(c); return 1; }
@@ -621,10 +649,11 @@ int blk_set_state(blk_ctx *c, const uint32_t *v, const uint32_t *p, int32_t n_it
         if (!c || !v) return fail("blk_set_state: null argument");
         CU(cudaSetDevice(c->device));
         const int np = c->geo.np, n = c->geo.n;
-        if (upload_rows(c, c->v, v, c->N)) return 1;
+        if (upload_rows(c, c->v, v, c->N, c->n_new2old)) return 1;
         int64_t ln = c->n1() - c->n0();
         if (p) {
-                if (upload_rows(c, c->p, p + (size_t)c->n0() * n, ln)) return 1;
+                // (maps exist only when world == 1, where the local block is the whole dimension)
+                if (upload_rows(c, c->p, p + (size_t)c->n0() * n, ln, c->n_new2old)) return 1;
         } else {
                 CU(cudaMemsetAsync(c->p, 0, sizeof(u32) * (size_t)(ln > 0 ? ln : 1) * np, c->stream));
         }
@@ -700,12 +729,12 @@ int blk_get_state(blk_ctx *c, uint32_t *v, uint32_t *tmp, uint32_t *Av, uint32_t
         const u32 *vsrc = nullptr;
         if (v) {
                 // straight into the caller's buffer (fast when it is pinned)
-                if (download_rows(c, v, c->v, N)) return 1;
+                if (download_rows(c, v, c->v, N, c->n_old2new)) return 1;
                 memset(v + (size_t)N * n, 0, sizeof(u32) * (size_t)(pad - N * n));
                 vsrc = v;
         } else if (tmp) {
                 hv.resize((size_t)N * n);
-                if (download_rows(c, hv.data(), c->v, N)) return 1;
+                if (download_rows(c, hv.data(), c->v, N, c->n_old2new)) return 1;
                 vsrc = hv.data();
         }
         if (tmp) {
@@ -731,7 +760,7 @@ int blk_get_state(blk_ctx *c, uint32_t *v, uint32_t *tmp, uint32_t *Av, uint32_t
                 memset(dst, 0, sizeof(u32) * (size_t)pad);
                 u32 *src = which ? c->p : c->Av;
                 if (c->world == 1) {
-                        if (download_rows(c, dst, src, N)) return 1;
+                        if (download_rows(c, dst, src, N, c->n_old2new)) return 1;
                 } else {
                         u32 *full = nullptr;
                         CU(cudaMalloc(&full, sizeof(u32) * (size_t)gather_cap(c->n_off) * np));
@@ -787,7 +816,7 @@ int blk_spmv(blk_ctx *c, uint32_t *y, const uint32_t *x, int32_t transpose)
         u32 *dx = nullptr, *dy = nullptr;
         CU(cudaMalloc(&dx, sizeof(u32) * (size_t)in_rows * np));
         CU(cudaMalloc(&dy, sizeof(u32) * (size_t)gather_cap(off) * np));
-        int rc = upload_rows(c, dx, x, in_rows);
+        int rc = upload_rows(c, dx, x, in_rows, s1 ? c->n_new2old : nullptr);
         if (!rc) {
                 // poison the output: every row must be written by the kernels
                 cudaMemsetAsync(dy, 0xff, sizeof(u32) * (size_t)out_rows * np, c->stream);
@@ -795,7 +824,7 @@ int blk_spmv(blk_ctx *c, uint32_t *y, const uint32_t *x, int32_t transpose)
                 c->launches += k;
                 if (c->world > 1) rc = allgather_rows(c, dy, off);
         }
-        if (!rc) rc = download_rows(c, y, dy, out_rows);
+        if (!rc) rc = download_rows(c, y, dy, out_rows, s1 ? nullptr : c->n_old2new);
         cudaError_t e = cudaGetLastError();
         cudaFree(dx); cudaFree(dy);
         if (!rc && e != cudaSuccess) return fail(std::string("blk_spmv: ") + cudaGetErrorString(e));

@@ -249,21 +249,25 @@ k_ortho(int64_t rows, const u32 *v, const u32 *__restrict__ Av, const u32 *p, u3
         }
 }
 
-__global__ void k_pad_rows(const u32 *__restrict__ src, u32 *__restrict__ dst, int64_t rows, int n, int np)
+__global__ void k_pad_rows(const u32 *__restrict__ src, u32 *__restrict__ dst, int64_t rows, int n, int np,
+                           const u32 *__restrict__ map)
 {
         int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
         if (e >= rows * np) return;
         int64_t r = e / np;
         int j = (int)(e - r * np);
-        dst[e] = j < n ? src[r * n + j] : 0u;
+        int64_t sr = map ? map[r] : r;
+        dst[e] = j < n ? src[sr * n + j] : 0u;
 }
-__global__ void k_unpad_rows(const u32 *__restrict__ src, u32 *__restrict__ dst, int64_t rows, int n, int np)
+__global__ void k_unpad_rows(const u32 *__restrict__ src, u32 *__restrict__ dst, int64_t rows, int n, int np,
+                             const u32 *__restrict__ map)
 {
         int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
         if (e >= rows * n) return;
         int64_t r = e / n;
         int j = (int)(e - r * n);
-        dst[e] = src[r * np + j];
+        int64_t sr = map ? map[r] : r;
+        dst[e] = src[sr * np + j];
 }
 
 template <int NP>
@@ -367,17 +371,17 @@ void dense_prepare(const Geometry &geo, const ModP &m)
         dense_mma_prepare(geo.np);
 }
 
-int launch_pad_rows(const u32 *src, u32 *dst, int64_t rows, int n, int np, cudaStream_t st)
+int launch_pad_rows(const u32 *src, u32 *dst, int64_t rows, int n, int np, const u32 *map, cudaStream_t st)
 {
         int64_t tot = rows * np;
         if (tot == 0) return 0;
-        k_pad_rows<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(src, dst, rows, n, np);
+        k_pad_rows<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(src, dst, rows, n, np, map);
         return 1;
 }
-int launch_unpad_rows(const u32 *src, u32 *dst, int64_t rows, int n, int np, cudaStream_t st)
+int launch_unpad_rows(const u32 *src, u32 *dst, int64_t rows, int n, int np, const u32 *map, cudaStream_t st)
 {
         int64_t tot = rows * n;
         if (tot == 0) return 0;
-        k_unpad_rows<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(src, dst, rows, n, np);
+        k_unpad_rows<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(src, dst, rows, n, np, map);
         return 1;
 }

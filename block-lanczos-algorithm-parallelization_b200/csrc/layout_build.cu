@@ -22,7 +22,7 @@ inline unsigned nblk(int64_t n) { return (unsigned)((n + TB - 1) / TB); }
 __global__ void k_make_keys(int64_t nnz, const int32_t *__restrict__ row, const int32_t *__restrict__ col,
                             const u32 *__restrict__ val, int64_t row_lo, int64_t rows, int64_t cols, u32 p,
                             u64 *__restrict__ keys, u32 *__restrict__ vals, u32 *__restrict__ cnt,
-                            int *__restrict__ bad)
+                            int *__restrict__ bad, const u32 *__restrict__ row_map, const u32 *__restrict__ col_map)
 {
         int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
         if (s >= nnz) return;
@@ -32,6 +32,8 @@ __global__ void k_make_keys(int64_t nnz, const int32_t *__restrict__ row, const 
                 *bad = 1;
                 r = 0; c = 0;
         }
+        if (row_map) r = row_map[r];                 // relabelling (single-GPU: row_lo == 0)
+        if (col_map) c = col_map[c];
         keys[s] = ((u64)r << 32) | (u64)c;
         vals[s] = val[s] % p;                       // Mx[u] = x % prime, sequential/lanczos_modp.c:243
         atomicAdd(&cnt[r], 1u);
@@ -141,7 +143,7 @@ static int pick_chunk_len(int64_t stored, int G)
 
 std::string build_operator(SpOp *op, const Geometry &geo, int chunk_len, int64_t rows, int64_t cols,
                            int64_t row_lo, int64_t nnz, const int32_t *d_row, const int32_t *d_col,
-                           const u32 *d_val, u32 prime, cudaStream_t st)
+                           const u32 *d_val, u32 prime, const u32 *row_map, const u32 *col_map, cudaStream_t st)
 {
         *op = SpOp();
         op->rows = rows; op->cols = cols; op->nnz = nnz; op->G = geo.G;
@@ -182,7 +184,7 @@ std::string build_operator(SpOp *op, const Geometry &geo, int chunk_len, int64_t
         }
         if (nnz > 0) {
                 k_make_keys<<<nblk(nnz), TB, 0, st>>>(nnz, d_row, d_col, d_val, row_lo, rows, cols, prime,
-                                                      keys[0], vals[0], cnt, bad);
+                                                      keys[0], vals[0], cnt, bad, row_map, col_map);
                 CKC(cudaGetLastError());
         }
         int h_bad = 0;
@@ -256,4 +258,72 @@ std::string build_operator(SpOp *op, const Geometry &geo, int chunk_len, int64_t
         cleanup();
         return "";
 #undef CKC
+}
+
+// ---------------------------------------------------------------------------------------------
+// Degree-sorted relabelling of one dimension: new label 0 = the index that occurs most often.
+// The Lanczos vectors can be stored under any row order (dots are order-free, orthogonalize is
+// row-wise); putting the high-degree rows first makes the rows that the product S1 gathers most
+// often one contiguous prefix that fits L2 (and packs two hot 64-byte rows per 128-byte line).
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void k_count_index(int64_t nnz, const int32_t *__restrict__ idx, int64_t dim, u32 *__restrict__ cnt)
+{
+        int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (s >= nnz) return;
+        int64_t r = idx[s];
+        if (r >= 0 && r < dim) atomicAdd(&cnt[r], 1u);
+}
+__global__ void k_sort_keys(int64_t dim, const u32 *__restrict__ cnt, u32 *__restrict__ key, u32 *__restrict__ val)
+{
+        int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (r >= dim) return;
+        key[r] = ~cnt[r];            // ascending sort of ~cnt = descending degree; radix sort is stable
+        val[r] = (u32)r;
+}
+__global__ void k_invert_perm(int64_t dim, const u32 *__restrict__ new2old, u32 *__restrict__ old2new)
+{
+        int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (s >= dim) return;
+        old2new[new2old[s]] = (u32)s;
+}
+}  // namespace
+
+std::string degree_sort_maps(int64_t nnz, const int32_t *d_idx, int64_t dim, u32 **old2new, u32 **new2old,
+                             cudaStream_t st)
+{
+        *old2new = *new2old = nullptr;
+        u32 *cnt = nullptr, *key[2] = {nullptr, nullptr}, *val[2] = {nullptr, nullptr};
+        void *tmp = nullptr;
+        auto cleanup = [&]() { cudaFree(cnt); cudaFree(key[0]); cudaFree(key[1]); cudaFree(val[0]); cudaFree(val[1]); cudaFree(tmp); };
+#define CKD(call)                                                                                  \
+        do {                                                                                       \
+                cudaError_t e_ = (call);                                                           \
+                if (e_ != cudaSuccess) {                                                           \
+                        std::string err = std::string(#call) + ": " + cudaGetErrorString(e_);      \
+                        cleanup(); cudaFree(*old2new); cudaFree(*new2old); *old2new = *new2old = nullptr; \
+                        return err;                                                                \
+                }                                                                                  \
+        } while (0)
+        size_t b = sizeof(u32) * (size_t)dim;
+        CKD(cudaMalloc(&cnt, b));
+        for (int q = 0; q < 2; q++) { CKD(cudaMalloc(&key[q], b)); CKD(cudaMalloc(&val[q], b)); }
+        CKD(cudaMalloc(old2new, b));
+        CKD(cudaMalloc(new2old, b));
+        CKD(cudaMemsetAsync(cnt, 0, b, st));
+        if (nnz) k_count_index<<<nblk(nnz), TB, 0, st>>>(nnz, d_idx, dim, cnt);
+        k_sort_keys<<<nblk(dim), TB, 0, st>>>(dim, cnt, key[0], val[0]);
+        CKD(cudaGetLastError());
+        cub::DoubleBuffer<u32> dk(key[0], key[1]), dv(val[0], val[1]);
+        size_t tb = 0;
+        CKD(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, dim, 0, 32, st));
+        CKD(cudaMalloc(&tmp, tb ? tb : 16));
+        CKD(cub::DeviceRadixSort::SortPairs(tmp, tb, dk, dv, dim, 0, 32, st));
+        CKD(cudaMemcpyAsync(*new2old, dv.Current(), b, cudaMemcpyDeviceToDevice, st));
+        k_invert_perm<<<nblk(dim), TB, 0, st>>>(dim, *new2old, *old2new);
+        CKD(cudaGetLastError());
+        CKD(cudaStreamSynchronize(st));
+        cleanup();
+        return "";
+#undef CKD
 }

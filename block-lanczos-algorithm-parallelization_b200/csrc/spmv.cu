@@ -23,17 +23,16 @@ template <> struct Vec<1> { typedef unsigned int T; };
 template <> struct Vec<2> { typedef uint2 T; };
 template <> struct Vec<4> { typedef uint4 T; };
 
-// Gather of one x row segment.  LD selects the cache policy (tuning knob BLK_GATHER_MODE):
-//   0 ld.global.nc   1 ld.global.cg (L2 only)   2 ld.global.nc.L1::no_allocate
-//   3 ld.global.nc.L1::no_allocate.L2::64B
-template <int V, int LD> __device__ __forceinline__ void load_vec(u32 (&o)[V], const u32 *p)
+// Gather of one x row segment.  HOT = 1: x rows below `hot` (the high-degree prefix of a
+// degree-sorted dimension) are loaded with an L2 evict_last policy, everything else with
+// evict_first, so that the part of x that is gathered over and over stays resident while the
+// once-only traffic streams through (tools/hot_gather.cu).
+template <int V, int HOT> __device__ __forceinline__ void load_vec(u32 (&o)[V], const u32 *p, u64 pol)
 {
-        if (V == 4) {
+        if (V == 4 && HOT) {
                 u32 a, b, c, d;
-                if (LD == 1) asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p));
-                else if (LD == 2) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p));
-                else if (LD == 3) asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p));
-                else asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p));
+                asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                             : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p), "l"(pol));
                 o[0] = a; o[1 % V] = b; o[2 % V] = c; o[3 % V] = d;
         } else {
                 typename Vec<V>::T t = __ldg(reinterpret_cast<const typename Vec<V>::T *>(p));
@@ -58,12 +57,17 @@ template <int V> __device__ __forceinline__ void store_vec(u32 *p, const u32 (&o
         *reinterpret_cast<typename Vec<V>::T *>(p) = t;
 }
 
-template <int L, int V, int FOLD, int LD>
+template <int L, int V, int FOLD, int HOT>
 __global__ void __launch_bounds__(WARPS * 32)
 k_spmv(const uint2 *__restrict__ ent, const u32 *__restrict__ chunk_row, u32 *__restrict__ whead,
        int64_t ntiles, int Q, u32 rows, const u32 *__restrict__ x, u32 *__restrict__ y, ModP m,
-       const DevSmall *__restrict__ state)
+       const DevSmall *__restrict__ state, u32 hot)
 {
+        u64 pol_hot = 0, pol_cold = 0;
+        if (HOT) {
+                asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_hot));
+                asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_cold));
+        }
         constexpr int G = 32 / L;
         constexpr int NP = L * V;
         if (state && state->halt) return;
@@ -93,7 +97,10 @@ k_spmv(const uint2 *__restrict__ ent, const u32 *__restrict__ chunk_row, u32 *__
                 u32 xv[U][V];
 #pragma unroll
                 for (int u = 0; u < U; u++)
-                        load_vec<V, LD>(xv[u], xs + (size_t)(ee[u].x & 0x7fffffffu) * NP);
+                {
+                        const u32 col = ee[u].x & 0x7fffffffu;
+                        load_vec<V, HOT>(xv[u], xs + (size_t)col * NP, col < hot ? pol_hot : pol_cold);
+                }
 #pragma unroll
                 for (int u = 0; u < U; u++) {
 #pragma unroll
@@ -199,41 +206,22 @@ k_spmv_fix(const u32 *__restrict__ tail_row, const u32 *__restrict__ span, const
         store_vec<V>(y + (size_t)r * NP + sub * V, cur);
 }
 
-template <int L, int V, int LD>
-void launch_ld(const SpOp &op, const ModP &m, const u32 *x, u32 *y, const DevSmall *state, cudaStream_t st)
+template <int L, int V, int HOT>
+void launch_hot(const SpOp &op, const ModP &m, const u32 *x, u32 *y, const DevSmall *state, cudaStream_t st)
 {
         unsigned blocks = (unsigned)((op.ntiles + WARPS - 1) / WARPS);
         switch (m.fold_every) {
-        case 0: k_spmv<L, V, 0, LD><<<blocks, WARPS * 32, 0, st>>>(op.ent, op.chunk_row, op.whead, op.ntiles, op.Q, (u32)op.rows, x, y, m, state); break;
-        case 8: k_spmv<L, V, 8, LD><<<blocks, WARPS * 32, 0, st>>>(op.ent, op.chunk_row, op.whead, op.ntiles, op.Q, (u32)op.rows, x, y, m, state); break;
-        default: k_spmv<L, V, 2, LD><<<blocks, WARPS * 32, 0, st>>>(op.ent, op.chunk_row, op.whead, op.ntiles, op.Q, (u32)op.rows, x, y, m, state); break;
+        case 0: k_spmv<L, V, 0, HOT><<<blocks, WARPS * 32, 0, st>>>(op.ent, op.chunk_row, op.whead, op.ntiles, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols); break;
+        case 8: k_spmv<L, V, 8, HOT><<<blocks, WARPS * 32, 0, st>>>(op.ent, op.chunk_row, op.whead, op.ntiles, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols); break;
+        default: k_spmv<L, V, 2, HOT><<<blocks, WARPS * 32, 0, st>>>(op.ent, op.chunk_row, op.whead, op.ntiles, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols); break;
         }
-}
-
-int gather_mode()
-{
-        static int mode = -1;
-        if (mode < 0) {
-                const char *e = getenv("BLK_GATHER_MODE");
-                mode = e ? atoi(e) : 0;
-                if (mode < 0 || mode > 3) mode = 0;
-        }
-        return mode;
 }
 
 template <int L, int V>
 int launch_lv(const SpOp &op, const ModP &m, const u32 *x, u32 *y, const DevSmall *state, cudaStream_t st)
 {
-        if (V == 4) {
-                switch (gather_mode()) {
-                case 1: launch_ld<L, V, 1>(op, m, x, y, state, st); break;
-                case 2: launch_ld<L, V, 2>(op, m, x, y, state, st); break;
-                case 3: launch_ld<L, V, 3>(op, m, x, y, state, st); break;
-                default: launch_ld<L, V, 0>(op, m, x, y, state, st); break;
-                }
-        } else {
-                launch_ld<L, V, 0>(op, m, x, y, state, st);
-        }
+        if (V == 4 && op.hot_cols > 0) launch_hot<L, V, 1>(op, m, x, y, state, st);
+        else launch_hot<L, V, 0>(op, m, x, y, state, st);
         int64_t threads = op.ntiles * L;
         k_spmv_fix<L, V><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(op.tail_row, op.span, op.whead, op.ntiles, y, m, state);
         return 2;

@@ -229,3 +229,37 @@ def test_bad_input_is_an_error_not_a_crash(lib):
         lib.BlockLanczos(M, n=2, prime=2 ** 31 + 11)
     with pytest.raises(lib.BlkError, match="blocking factor"):
         lib.BlockLanczos(M, n=65, prime=65537)
+
+
+@pytest.fixture
+def forced_relabel(monkeypatch):
+    """Force the degree-sorted relabelling + L2 hot-prefix gathers (normally only for blocks that
+    exceed L2) on the small test matrices."""
+    monkeypatch.setenv("BLK_HOT_MIN_BYTES", "0")
+    monkeypatch.setenv("BLK_HOT_BYTES", "4096")
+
+
+@pytest.mark.parametrize("n,p", [(4, P_FERMAT), (16, P_MERSENNE), (5, P_CAP), (32, P_MERSENNE)])
+def test_relabelled_layout_is_invisible(lib, oracle, forced_relabel, n, p):
+    rng = np.random.default_rng(n)
+    for name, M in matrices(lib).items():
+        Mp = M.reduced(p)
+        with lib.BlockLanczos(Mp, n=n, prime=p) as ctx:
+            for tr in (False, True):
+                cols = M.nrows if tr else M.ncols
+                x = rng.integers(0, p, size=cols * n).astype(np.uint32)
+                assert np.array_equal(ctx.sparse_matrix_vector_product(x, tr),
+                                      oracle.sparse_matrix_vector_product(Mp, x, tr, n, p)), (name, tr)
+    for right in (False, True):
+        M = lib.synth.powerlaw_rows(700, 640, mean=7, seed=77, with_empty_rows=9).reduced(p)
+        N = M.ncols if right else M.nrows
+        v0 = oracle.start_block(N * n, p)
+        with lib.BlockLanczos(M, n=n, prime=p, right=right) as ctx:
+            got = ctx.block_lanczos(v0, stop_after=6, batch=4)
+            want = oracle.lanczos_run(M, n, p, right, stop_after=6)
+            for k in ("v", "tmp", "Av", "p"):
+                assert np.array_equal(got[k], want[k]), (right, k)
+            full = ctx.block_lanczos(v0)
+            ref = oracle.lanczos_run(M, n, p, right)
+            assert full["iters"] == ref["iters"] and np.array_equal(full["v"], ref["v"]) and \
+                np.array_equal(full["tmp"], ref["tmp"])
