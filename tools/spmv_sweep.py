@@ -11,15 +11,21 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--rows", type=int, default=50_000_000)
 ap.add_argument("--reps", type=int, default=10)
 ap.add_argument("--out", default="gpurun_out/spmv_sweep.json")
+ap.add_argument("--band", type=int, default=0, help="columns within +-band of the row (locality test); 0 = uniform")
+ap.add_argument("--ns", type=int, nargs="+", default=[1, 2, 4, 8, 16, 32])
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 w = dict(rows=a.rows, cols=a.rows, mean=30.0)
 rows, cols, vals, nnz = bench.gen_device_coo(torch, w, dev)
+if a.band:
+    off = torch.randint(-a.band, a.band + 1, (nnz,), device=dev, dtype=torch.int32)
+    cols = torch.clamp(rows + off, 0, a.rows - 1).to(torch.int32)
+    del off
 torch.cuda.synchronize()
 peak, _ = bench.peaks()
 res = []
 for p in (65537, 2147483647):
-    for n in (1, 2, 4, 8, 16, 32):
+    for n in a.ns:
         ctx = B.BlockLanczos(n=n, prime=p, right=False,
                              device_coo=(a.rows, a.rows, nnz, rows.data_ptr(), cols.data_ptr(), vals.data_ptr()))
         v0 = torch.randint(0, p, (a.rows * n,), dtype=torch.int64).to(torch.int32).numpy().view("uint32")
@@ -38,4 +44,4 @@ for p in (65537, 2147483647):
             res.append(rec)
             print(json.dumps(rec), flush=True)
         ctx.close()
-json.dump(dict(rows=a.rows, nnz=nnz, peak_GBs=peak, results=res), open(a.out, "w"), indent=1)
+json.dump(dict(rows=a.rows, nnz=nnz, band=a.band, peak_GBs=peak, results=res), open(a.out, "w"), indent=1)
