@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <vector>
 #include "modp.cuh"
 
 // ----------------------------------------------------------------------------------------------
@@ -37,6 +38,10 @@ struct SpOp {
         u32 *span = nullptr;       // [ntiles]    number of following tiles that finish that row (0: none)
         u32 *whead = nullptr;      // [ntiles*n_pad] scratch: the tile's contribution to a row opened earlier
         size_t bytes = 0;
+        // Row pieces for pipelining a product with the exchange of its result (multi-GPU): piece q is
+        // tiles [piece_tile[q], piece_tile[q+1]); after its fix-up, rows [piece_row[q], piece_row[q+1])
+        // are final.  piece_scan[q] <= piece_tile[q] is the first tile whose open row ends in piece q.
+        std::vector<int64_t> piece_tile, piece_row, piece_scan;
         u32 hot_cols = 0;          // > 0: x rows [0, hot_cols) are gathered with L2 evict_last, the rest evict_first
 };
 
@@ -75,15 +80,17 @@ static inline Geometry make_geometry(int n)
 // layout_build.cu
 std::string build_operator(SpOp *op, const Geometry &geo, int chunk_len, int64_t rows, int64_t cols,
                            int64_t row_lo, int64_t nnz, const int32_t *d_row, const int32_t *d_col,
-                           const u32 *d_val, u32 prime, const u32 *row_map, const u32 *col_map, cudaStream_t st);
+                           const u32 *d_val, u32 prime, const u32 *row_map, const u32 *col_map, int pieces,
+                           cudaStream_t st);
 void free_operator(SpOp *op);
 // old->new / new->old labels of one dimension sorted by decreasing number of entries
 std::string degree_sort_maps(int64_t nnz, const int32_t *d_idx, int64_t dim, u32 **old2new, u32 **new2old,
                              cudaStream_t st);
 
 // spmv.cu
+// piece < 0: the whole operator; else only tiles (and the fix-up) of that row piece
 int launch_spmv(const SpOp &op, const Geometry &geo, const ModP &m, const u32 *x, u32 *y,
-                const DevSmall *state, cudaStream_t st);
+                const DevSmall *state, cudaStream_t st, int piece = -1);
 
 // dense.cu
 int dots_num_blocks(int64_t rows, int np);

@@ -107,6 +107,13 @@ struct blk_ctx {
         cudaStream_t stream = nullptr;
         bool own_stream = false;
         ncclComm_t comm = nullptr;
+        // pipelined product 1 (multi-GPU): S1 runs in row pieces; each finished piece is broadcast on
+        // comm_stream while the next one is computed
+        int pieces = 1;
+        cudaStream_t comm_stream = nullptr;
+        std::vector<cudaEvent_t> ev_piece;
+        cudaEvent_t ev_comm = nullptr;
+        std::vector<int64_t> piece_rows_all;     // [world][pieces+1] local row boundaries of every rank's S1
         ncclResult_t (*nccl_allgather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
         // loop bookkeeping
         int iters = 0, stopped = 0;
@@ -265,13 +272,38 @@ int enqueue_iteration(blk_ctx *c, EventTimer *tm)
                 if (tm) tm->end(c, 0);
         }
         if (tm) tm->begin(c, BLK_PH_SPMV1);
-        k = launch_spmv(c->S1, g, c->m, c->v, c->tmp + (size_t)c->m0() * np, c->state, c->stream);
-        c->launches += k;
-        if (tm) tm->end(c, k);
-        if (c->world > 1) {
-                if (tm) tm->begin(c, BLK_PH_EXCHANGE);
-                if (allgather_rows(c, c->tmp, c->m_off)) return 1;
+        if (c->world > 1 && c->pieces > 1) {
+                // product 1 in row pieces; piece q is broadcast by its owners while piece q+1 is computed
+                const int K = c->pieces;
+                k = 0;
+                for (int q = 0; q < K; q++) {
+                        k += launch_spmv(c->S1, g, c->m, c->v, c->tmp + (size_t)c->m0() * np, c->state, c->stream, q);
+                        CU(cudaEventRecord(c->ev_piece[q], c->stream));
+                        CU(cudaStreamWaitEvent(c->comm_stream, c->ev_piece[q], 0));
+                        NC(g_nccl.GroupStart());
+                        for (int r = 0; r < c->world; r++) {
+                                int64_t lo = c->piece_rows_all[(size_t)r * (K + 1) + q], hi = c->piece_rows_all[(size_t)r * (K + 1) + q + 1];
+                                size_t cnt = (size_t)(hi - lo) * np;
+                                u32 *ptr = c->tmp + (size_t)(c->m_off[r] + lo) * np;
+                                if (cnt) NC(g_nccl.Broadcast(ptr, ptr, cnt, ncclUint32, r, c->comm, c->comm_stream));
+                        }
+                        NC(g_nccl.GroupEnd());
+                }
+                c->launches += k;
+                if (tm) tm->end(c, k);
+                if (tm) tm->begin(c, BLK_PH_EXCHANGE);          // only the part of the exchange that is not hidden
+                CU(cudaEventRecord(c->ev_comm, c->comm_stream));
+                CU(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
                 if (tm) tm->end(c, 0);
+        } else {
+                k = launch_spmv(c->S1, g, c->m, c->v, c->tmp + (size_t)c->m0() * np, c->state, c->stream);
+                c->launches += k;
+                if (tm) tm->end(c, k);
+                if (c->world > 1) {
+                        if (tm) tm->begin(c, BLK_PH_EXCHANGE);
+                        if (allgather_rows(c, c->tmp, c->m_off)) return 1;
+                        if (tm) tm->end(c, 0);
+                }
         }
         if (tm) tm->begin(c, BLK_PH_SPMV2);
         k = launch_spmv(c->S2, g, c->m, c->tmp, c->Av, c->state, c->stream);
@@ -442,6 +474,9 @@ int blk_destroy(blk_ctx *c)
         cudaFree(c->mats); cudaFree(c->sums); cudaFree(c->state); cudaFree(c->dots_counter);
         cudaFree(c->n_old2new); cudaFree(c->n_new2old);
         if (c->h_state) cudaFreeHost(c->h_state);
+        for (auto e : c->ev_piece) cudaEventDestroy(e);
+        if (c->ev_comm) cudaEventDestroy(c->ev_comm);
+        if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
         if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
         delete c;
         return 0;
@@ -553,6 +588,13 @@ int blk_create(blk_ctx **out, const blk_params *prm)
 
         // ---- the two operators.  S1: rows = my block of the Mc dimension, columns = N dimension;
         //      S2: rows = my block of the N dimension, columns = Mc dimension.
+        int want_pieces = 1;
+        if (world > 1) {
+                const char *e = getenv("BLK_PIECES");
+                want_pieces = e ? atoi(e) : 8;
+                if (want_pieces < 1) want_pieces = 1;
+                if (want_pieces > 32) want_pieces = 32;
+        }
         for (int which = 0; which < 2; which++) {
                 SpOp *op = which ? &c->S2 : &c->S1;
                 const int32_t *rk = which ? idxN : idxM, *ck = which ? idxM : idxN;
@@ -561,7 +603,7 @@ int blk_create(blk_ctx **out, const blk_params *prm)
                 std::string err;
                 if (world == 1) {
                         err = build_operator(op, c->geo, prm->chunk_len, hi - lo, cols, lo, nnz, rk, ck, dx, m.p,
-                                             which ? c->n_old2new : nullptr, which ? nullptr : c->n_old2new, c->stream);
+                                             which ? c->n_old2new : nullptr, which ? nullptr : c->n_old2new, 1, c->stream);
                         if (!which) op->hot_cols = (u32)c->hot_rows;
                 } else {
                         int32_t *sr = nullptr, *sc = nullptr; u32 *sx = nullptr;
@@ -590,7 +632,8 @@ int blk_create(blk_ctx **out, const blk_params *prm)
                         CUX(cudaStreamSynchronize(c->stream));
                         cudaFree(cnt);
                         if ((int64_t)hcnt != sel) err = "shard selection count mismatch";
-                        else err = build_operator(op, c->geo, prm->chunk_len, hi - lo, cols, lo, sel, sr, sc, sx, m.p, nullptr, nullptr, c->stream);
+                        else err = build_operator(op, c->geo, prm->chunk_len, hi - lo, cols, lo, sel, sr, sc, sx, m.p, nullptr, nullptr,
+                                                       which ? 1 : want_pieces, c->stream);
                         cudaFree(sr); cudaFree(sc); cudaFree(sx);
                 }
                 if (!err.empty()) { free_coo(); fail(err); blk_destroy(c); return 1; }
@@ -638,6 +681,41 @@ int blk_create(blk_ctx **out, const blk_params *prm)
                 }
                 const char *e = getenv("BLK_ALLGATHER");
                 if (!(e && e[0] == 'b')) c->nccl_allgather = g_nccl.AllGather;     // BLK_ALLGATHER=bcast forces broadcasts
+                // every rank needs every rank's piece boundaries of S1 (number of pieces = the minimum)
+                {
+                        const int KMAX = 32;
+                        std::vector<long long> mine(KMAX + 2, 0), all((size_t)(KMAX + 2) * world, 0);
+                        int K = (int)c->S1.piece_tile.size() - 1;
+                        mine[0] = K;
+                        for (int k = 0; k <= K; k++) mine[1 + k] = c->S1.piece_row[k];
+                        long long *dbuf = nullptr;
+                        CUX(cudaMalloc(&dbuf, sizeof(long long) * all.size()));
+                        CUX(cudaMemcpyAsync(dbuf + (size_t)c->rank * (KMAX + 2), mine.data(), sizeof(long long) * (KMAX + 2),
+                                            cudaMemcpyHostToDevice, c->stream));
+                        ncclResult_t r2 = g_nccl.AllGather(dbuf + (size_t)c->rank * (KMAX + 2), dbuf, (size_t)(KMAX + 2), ncclInt64,
+                                                            c->comm, c->stream);
+                        if (r2 != ncclSuccess) { fail(std::string("ncclAllGather: ") + g_nccl.GetErrorString(r2)); blk_destroy(c); return 1; }
+                        CUX(cudaMemcpyAsync(all.data(), dbuf, sizeof(long long) * all.size(), cudaMemcpyDeviceToHost, c->stream));
+                        CUX(cudaStreamSynchronize(c->stream));
+                        cudaFree(dbuf);
+                        bool same = true;
+                        for (int r = 0; r < world; r++) same = same && all[(size_t)r * (KMAX + 2)] == K;
+                        c->pieces = same ? K : 1;            // all ranks must agree on the schedule
+                        if (c->pieces > 1) {
+                                c->piece_rows_all.assign((size_t)world * (K + 1), 0);
+                                for (int r = 0; r < world; r++)
+                                        for (int k = 0; k <= K; k++)
+                                                c->piece_rows_all[(size_t)r * (K + 1) + k] = all[(size_t)r * (KMAX + 2) + 1 + k];
+                                // highest priority: the block scheduler then places NCCL's few large CTAs ahead
+                                // of the thousands of queued SpMV blocks instead of after them
+                                int pr_least = 0, pr_greatest = 0;
+                                CUX(cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest));
+                                CUX(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, pr_greatest));
+                                c->ev_piece.resize(K);
+                                for (auto &ev : c->ev_piece) CUX(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                                CUX(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
+                        }
+                }
         }
 #undef CUX
         *out = c;

@@ -143,7 +143,8 @@ static int pick_chunk_len(int64_t stored, int G)
 
 std::string build_operator(SpOp *op, const Geometry &geo, int chunk_len, int64_t rows, int64_t cols,
                            int64_t row_lo, int64_t nnz, const int32_t *d_row, const int32_t *d_col,
-                           const u32 *d_val, u32 prime, const u32 *row_map, const u32 *col_map, cudaStream_t st)
+                           const u32 *d_val, u32 prime, const u32 *row_map, const u32 *col_map, int pieces,
+                           cudaStream_t st)
 {
         *op = SpOp();
         op->rows = rows; op->cols = cols; op->nnz = nnz; op->G = geo.G;
@@ -255,6 +256,31 @@ std::string build_operator(SpOp *op, const Geometry &geo, int chunk_len, int64_t
                                                       op->tail_row, op->span);
         CKC(cudaGetLastError());
         CKC(cudaStreamSynchronize(st));
+
+        // ---- row pieces (see SpOp): boundaries at tile multiples; the row that straddles a boundary
+        // is finished by the fix-up of the piece in which it ends
+        int K = pieces > 1 ? pieces : 1;
+        if (op->ntiles < 4 * (int64_t)K) K = 1;
+        op->piece_tile.assign(K + 1, 0); op->piece_row.assign(K + 1, 0); op->piece_scan.assign(K + 1, 0);
+        op->piece_tile[K] = op->ntiles; op->piece_row[K] = rows;
+        for (int k = 1; k < K; k++) op->piece_tile[k] = op->ntiles * k / K;
+        for (int k = 0; k <= K; k++) op->piece_scan[k] = op->piece_tile[k];
+        for (int k = 1; k < K; k++) {
+                u32 cr = 0;
+                CKC(cudaMemcpy(&cr, op->chunk_row + op->piece_tile[k] * op->G, sizeof(u32), cudaMemcpyDeviceToHost));
+                int64_t r = cr & 0x7fffffffu;
+                op->piece_row[k] = r < rows ? r : rows;
+                if ((cr >> 31) && r < rows) {             // row r is open across the boundary
+                        u64 start = 0;
+                        CKC(cudaMemcpy(&start, rowptr + r, sizeof(u64), cudaMemcpyDeviceToHost));
+                        int64_t ts = (int64_t)(start / (u64)tile);
+                        u32 sp = 0;
+                        CKC(cudaMemcpy(&sp, op->span + ts, sizeof(u32), cudaMemcpyDeviceToHost));
+                        int64_t te = ts + sp;
+                        for (int q = k; q < K && op->piece_tile[q] <= te; q++)
+                                if (ts < op->piece_scan[q]) op->piece_scan[q] = ts;
+                }
+        }
         cleanup();
         return "";
 #undef CKC

@@ -60,7 +60,7 @@ template <int V> __device__ __forceinline__ void store_vec(u32 *p, const u32 (&o
 template <int L, int V, int FOLD, int HOT>
 __global__ void __launch_bounds__(WARPS * 32)
 k_spmv(const uint2 *__restrict__ ent, const u32 *__restrict__ chunk_row, u32 *__restrict__ whead,
-       int64_t ntiles, int Q, u32 rows, const u32 *__restrict__ x, u32 *__restrict__ y, ModP m,
+       int64_t tile0, int64_t ntiles, int Q, u32 rows, const u32 *__restrict__ x, u32 *__restrict__ y, ModP m,
        const DevSmall *__restrict__ state, u32 hot)
 {
         u64 pol_hot = 0, pol_cold = 0;
@@ -72,7 +72,7 @@ k_spmv(const uint2 *__restrict__ ent, const u32 *__restrict__ chunk_row, u32 *__
         constexpr int NP = L * V;
         if (state && state->halt) return;
         const int lane = threadIdx.x & 31;
-        const int64_t t = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+        const int64_t t = tile0 + (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);      // tiles [tile0, ntiles)
         if (t >= ntiles) return;
         const int g = lane / L, sub = lane % L;
 
@@ -178,15 +178,18 @@ k_spmv(const uint2 *__restrict__ ent, const u32 *__restrict__ chunk_row, u32 *__
 template <int L, int V>
 __global__ void __launch_bounds__(256)
 k_spmv_fix(const u32 *__restrict__ tail_row, const u32 *__restrict__ span, const u32 *__restrict__ whead,
-           int64_t ntiles, u32 *__restrict__ y, ModP m, const DevSmall *__restrict__ state)
+           int64_t scan_lo, int64_t tile_lo, int64_t tile_hi, u32 *__restrict__ y, ModP m,
+           const DevSmall *__restrict__ state)
 {
+        // finishes the rows that END in tiles [tile_lo, tile_hi); such a row starts in a tile >= scan_lo
         constexpr int NP = L * V;
         if (state && state->halt) return;
-        int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / L;
+        int64_t gid = scan_lo + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / L;
         int sub = threadIdx.x % L;
-        if (gid >= ntiles) return;
+        if (gid >= tile_hi) return;
         u32 sp = __ldg(span + gid);
         if (sp == 0) return;
+        if (gid + sp >= tile_hi || gid + sp < tile_lo) return;      // ends in a later / an earlier piece
         u32 r = __ldg(tail_row + gid);
         u32 cur[V];
         load_vec_rw<V>(cur, y + (size_t)r * NP + sub * V);
@@ -207,39 +210,44 @@ k_spmv_fix(const u32 *__restrict__ tail_row, const u32 *__restrict__ span, const
 }
 
 template <int L, int V, int HOT>
-void launch_hot(const SpOp &op, const ModP &m, const u32 *x, u32 *y, const DevSmall *state, cudaStream_t st)
+void launch_hot(const SpOp &op, const ModP &m, const u32 *x, u32 *y, const DevSmall *state, cudaStream_t st,
+                int64_t t0, int64_t t1)
 {
-        unsigned blocks = (unsigned)((op.ntiles + WARPS - 1) / WARPS);
+        unsigned blocks = (unsigned)((t1 - t0 + WARPS - 1) / WARPS);
+        if (blocks == 0) return;
         switch (m.fold_every) {
-        case 0: k_spmv<L, V, 0, HOT><<<blocks, WARPS * 32, 0, st>>>(op.ent, op.chunk_row, op.whead, op.ntiles, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols); break;
-        case 8: k_spmv<L, V, 8, HOT><<<blocks, WARPS * 32, 0, st>>>(op.ent, op.chunk_row, op.whead, op.ntiles, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols); break;
-        default: k_spmv<L, V, 2, HOT><<<blocks, WARPS * 32, 0, st>>>(op.ent, op.chunk_row, op.whead, op.ntiles, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols); break;
+        case 0: k_spmv<L, V, 0, HOT><<<blocks, WARPS * 32, 0, st>>>(op.ent, op.chunk_row, op.whead, t0, t1, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols); break;
+        case 8: k_spmv<L, V, 8, HOT><<<blocks, WARPS * 32, 0, st>>>(op.ent, op.chunk_row, op.whead, t0, t1, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols); break;
+        default: k_spmv<L, V, 2, HOT><<<blocks, WARPS * 32, 0, st>>>(op.ent, op.chunk_row, op.whead, t0, t1, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols); break;
         }
 }
 
 template <int L, int V>
-int launch_lv(const SpOp &op, const ModP &m, const u32 *x, u32 *y, const DevSmall *state, cudaStream_t st)
+int launch_lv(const SpOp &op, const ModP &m, const u32 *x, u32 *y, const DevSmall *state, cudaStream_t st, int piece)
 {
-        if (V == 4 && op.hot_cols > 0) launch_hot<L, V, 1>(op, m, x, y, state, st);
-        else launch_hot<L, V, 0>(op, m, x, y, state, st);
-        int64_t threads = op.ntiles * L;
-        k_spmv_fix<L, V><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(op.tail_row, op.span, op.whead, op.ntiles, y, m, state);
+        int64_t t0 = 0, t1 = op.ntiles, scan = 0;
+        if (piece >= 0) { t0 = op.piece_tile[piece]; t1 = op.piece_tile[piece + 1]; scan = op.piece_scan[piece]; }
+        if (V == 4 && op.hot_cols > 0) launch_hot<L, V, 1>(op, m, x, y, state, st, t0, t1);
+        else launch_hot<L, V, 0>(op, m, x, y, state, st, t0, t1);
+        int64_t threads = (t1 - scan) * L;
+        if (threads > 0)
+                k_spmv_fix<L, V><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(op.tail_row, op.span, op.whead, scan, t0, t1, y, m, state);
         return 2;
 }
 
 }  // namespace
 
 int launch_spmv(const SpOp &op, const Geometry &geo, const ModP &m, const u32 *x, u32 *y,
-                const DevSmall *state, cudaStream_t st)
+                const DevSmall *state, cudaStream_t st, int piece)
 {
         switch (geo.np) {
-        case 1: return launch_lv<1, 1>(op, m, x, y, state, st);
-        case 2: return launch_lv<1, 2>(op, m, x, y, state, st);
-        case 4: return launch_lv<1, 4>(op, m, x, y, state, st);
-        case 8: return launch_lv<2, 4>(op, m, x, y, state, st);
-        case 16: return launch_lv<4, 4>(op, m, x, y, state, st);
-        case 32: return launch_lv<8, 4>(op, m, x, y, state, st);
-        case 64: return launch_lv<16, 4>(op, m, x, y, state, st);
+        case 1: return launch_lv<1, 1>(op, m, x, y, state, st, piece);
+        case 2: return launch_lv<1, 2>(op, m, x, y, state, st, piece);
+        case 4: return launch_lv<1, 4>(op, m, x, y, state, st, piece);
+        case 8: return launch_lv<2, 4>(op, m, x, y, state, st, piece);
+        case 16: return launch_lv<4, 4>(op, m, x, y, state, st, piece);
+        case 32: return launch_lv<8, 4>(op, m, x, y, state, st, piece);
+        case 64: return launch_lv<16, 4>(op, m, x, y, state, st, piece);
         }
         return -1;
 }
