@@ -24,6 +24,10 @@ struct ModP {
         u32 c32;      // 2^32 mod p
         u64 mu;       // floor(2^64 / p)
         int fold_every;
+        // short Barrett after one fold (see mp_reduce): valid when fast != 0
+        u32 fast;     // 1: (fold(x) >> s1) and mu2 fit 32 bits
+        u32 s1, t2;   // shifts
+        u32 mu2;      // floor(2^(s1+t2) / p)
 };
 
 // host: derive the constants; returns false if p is out of range
@@ -45,6 +49,33 @@ static inline bool modp_make(ModP *m, u64 p)
         else if (k >= 8.0L) m->fold_every = 8;
         else if (k >= 2.0L) m->fold_every = 2;
         else return false;
+        // Short reduction: x1 = fold(x) <= B1 = (2^32-1)(1+c32) < 2^XB.  With k = bits(p), s1 = k-3,
+        // t2 = XB+2-s1, mu2 = floor(2^(XB+2)/p):  qh = ((x1 >> s1) * mu2) >> t2 satisfies
+        // floor(x1/p) - 1 <= qh <= floor(x1/p)  (truncation errors 2^s1/p <= 1/4 and x1/2^(XB+2) < 1/4),
+        // so x1 - qh*p lies in [0, 2p) and can be formed in 32-bit arithmetic (2p <= 2^32).
+        // Usable when both factors fit 32 bits, i.e. XB - s1 <= 32: primes 2^k +- small, e.g.
+        // 2^31-1, 2^30-35, 65537.
+        m->fast = 0; m->s1 = m->t2 = 0; m->mu2 = 0;
+        {
+                long double b1 = 4294967295.0L * (1.0L + (long double)m->c32);
+                int xb = 1;
+                while (xb < 64 && b1 >= (long double)(1ull << xb) ) xb++;
+                if (b1 >= 18446744073709551616.0L) xb = 65;
+                int k = 0;
+                while ((p >> k) != 0) k++;
+                int s1 = k > 3 ? k - 3 : 0;
+                if (xb <= 64 && xb - s1 <= 32) {
+                        int e = xb + 2;
+                        u64 q = 0, r = 1;
+                        bool ok = true;
+                        for (int i = 0; i < e; i++) {          // q = floor(2^e / p) by long division
+                                r <<= 1; q <<= 1;
+                                if (r >= p) { r -= p; q += 1; }
+                                if (q >> 32) { ok = false; break; }
+                        }
+                        if (ok) { m->fast = 1; m->s1 = (u32)s1; m->t2 = (u32)(e - s1); m->mu2 = (u32)q; }
+                }
+        }
         return true;
 }
 
@@ -62,6 +93,14 @@ __device__ __forceinline__ void mp_fold(u64 &acc, const ModP &m)
 // canonical residue of any u64
 __device__ __forceinline__ u32 mp_reduce(u64 acc, const ModP &m)
 {
+        if (m.fast) {           // uniform branch: one fold, 32-bit Barrett, one conditional subtract
+                u64 x1 = (u64)(u32)acc + (u64)(u32)(acc >> 32) * (u64)m.c32;
+                u32 y = (u32)(x1 >> m.s1);
+                u32 qh = (u32)(((u64)y * (u64)m.mu2) >> m.t2);
+                u32 r = (u32)x1 - qh * m.p;
+                u32 r2 = r - m.p;
+                return r2 < r ? r2 : r;      // r < p: r - p wraps around
+        }
         u64 q = __umul64hi(acc, m.mu);
         u64 r = acc - q * (u64)m.p;
         if (r >= m.p) r -= m.p;
