@@ -58,9 +58,9 @@ def test_cli_output_file_identical_to_reference(driver, lib, tmp_path, name):
     assert checker(mtx, p, out, side) == bool(z["checker_ok"])
 
 
-@pytest.mark.parametrize("cfg", ["cfg1", "cfg2"])
+@pytest.mark.parametrize("cfg", ["cfg1", "cfg2", "cfg3"])
 def test_cli_full_baseline_config_identical_to_reference(driver, lib, tmp_path, cfg):
-    """BASELINE.json configs[0] and [1] at full size through the real CLI."""
+    """BASELINE.json configs[0], [1] and [2] at full size through the real CLI."""
     want = json.load(open(os.path.join(GOLDEN, "full_configs.json")))[cfg]
     M, a = lib.synth.baseline_config(int(cfg[3:]))
     mtx, out = str(tmp_path / "m.mtx"), str(tmp_path / "k.mtx")
