@@ -114,6 +114,22 @@ struct blk_ctx {
         std::vector<cudaEvent_t> ev_piece;
         cudaEvent_t ev_comm = nullptr;
         std::vector<int64_t> piece_rows_all;     // [world][pieces+1] local row boundaries of every rank's S1
+        std::vector<int64_t> piece_rows_all2;    // same for S2
+        int pieces2 = 1;
+        // "tmp recurrence" (multi-GPU): the next S1*v is obtained from S1*Av, so the vector that has to
+        // be exchanged is Av (hidden behind product 2) instead of the new v (which nothing could hide)
+        bool mg_recur = false, ran_since_set = false;
+        u32 *Av_full = nullptr;                  // gather target of Av; c->Av points at the local rows inside it
+        u32 *Tp = nullptr, *U = nullptr;         // local rows of S1*p and of S1*Av
+        u32 *tmp_prev = nullptr;                 // local rows of the previous tmp (only when Mc > N, for checkpoints)
+        // one-sided exchange: finished pieces are pushed into the peers' buffers by the copy engines
+        // (cudaMemcpyAsync on IPC-mapped peer pointers) -- no SMs taken from the sparse product, unlike
+        // NCCL's broadcast kernels; a (tiny) all-reduce that follows is the barrier
+        bool p2p = false;
+        std::vector<u32 *> peer_tmp, peer_av;    // [world] IPC mappings of every rank's tmp / Av_full (own = local)
+        std::vector<cudaStream_t> copy_streams;  // one per peer offset so that the copies use several copy engines
+        std::vector<cudaEvent_t> ev_copies;
+        u64 *barrier_word = nullptr;
         ncclResult_t (*nccl_allgather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
         // loop bookkeeping
         int iters = 0, stopped = 0;
@@ -260,9 +276,160 @@ int allgather_rows(blk_ctx *c, u32 *buf, const std::vector<int64_t> &off)
         return 0;
 }
 
+// broadcast piece q of a row-sharded block from every owner (grouped): rows_all = [world][K+1]
+int piece_broadcast(blk_ctx *c, u32 *buf, const std::vector<int64_t> &off, const std::vector<int64_t> &rows_all,
+                    int K, int q, cudaStream_t st)
+{
+        NC(g_nccl.GroupStart());
+        for (int r = 0; r < c->world; r++) {
+                int64_t lo = rows_all[(size_t)r * (K + 1) + q], hi = rows_all[(size_t)r * (K + 1) + q + 1];
+                size_t cnt = (size_t)(hi - lo) * c->geo.np;
+                u32 *ptr = buf + (size_t)(off[r] + lo) * c->geo.np;
+                if (cnt) NC(g_nccl.Broadcast(ptr, ptr, cnt, ncclUint32, r, c->comm, st));
+        }
+        NC(g_nccl.GroupEnd());
+        return 0;
+}
+
+// push my rows of piece q (finished when `ready` fires) into every peer's copy of the block: one copy
+// stream per peer offset (several copy engines), staggered so every receiver has one sender at a time
+int piece_push(blk_ctx *c, const std::vector<u32 *> &peers, const std::vector<int64_t> &off,
+               const std::vector<int64_t> &rows_all, int K, int q, cudaEvent_t ready)
+{
+        int64_t lo = rows_all[(size_t)c->rank * (K + 1) + q], hi = rows_all[(size_t)c->rank * (K + 1) + q + 1];
+        size_t bytes = sizeof(u32) * (size_t)(hi - lo) * c->geo.np;
+        size_t at = (size_t)(off[c->rank] + lo) * c->geo.np;
+        for (int s = 1; s < c->world; s++) {
+                int d = (c->rank + s) % c->world;
+                CU(cudaStreamWaitEvent(c->copy_streams[s - 1], ready, 0));
+                if (bytes) CU(cudaMemcpyAsync(peers[d] + at, peers[c->rank] + at, bytes, cudaMemcpyDeviceToDevice, c->copy_streams[s - 1]));
+        }
+        return 0;
+}
+
+// the main stream waits until all of this rank's pushes have left
+int pushes_done(blk_ctx *c)
+{
+        for (size_t s = 0; s < c->copy_streams.size(); s++) {
+                CU(cudaEventRecord(c->ev_copies[s], c->copy_streams[s]));
+                CU(cudaStreamWaitEvent(c->stream, c->ev_copies[s], 0));
+        }
+        return 0;
+}
+
+// Multi-GPU iteration.  Invariant at entry: tmp (full length, on every rank) = S1 v for the current
+// v, Tp (local rows) = S1 p.  Because S1 is linear and the n x n factors act on the right,
+//     S1 v' = sel(d, S1 Av, S1 v) + (S1 v) c + (S1 p) vtAvd,      S1 p' = sel(d, 0, S1 p) + (S1 v) winv
+// i.e. exactly orthogonalize() applied to (tmp, S1 Av, Tp).  All values are canonical residues, so
+// this is bit-identical to recomputing S1 v'.  What it buys: the only full-length vectors that
+// cross NVLink are Av and the new tmp, and both are produced by a sparse product that runs in
+// row pieces, so each piece travels while the next is computed; the new v is never gathered.
+int enqueue_iteration_mg(blk_ctx *c, EventTimer *tm)
+{
+        const Geometry &g = c->geo;
+        const int np = g.np;
+        int k = 0;
+        const int64_t lrows = c->n1() - c->n0();
+        u32 *vloc = c->v + (size_t)c->n0() * np;
+        u32 *tloc = c->tmp + (size_t)c->m0() * np;
+
+        // Av <- S2 tmp, piece by piece; every finished piece is broadcast while the next one runs
+        if (tm) tm->begin(c, BLK_PH_SPMV2);
+        for (int q = 0; q < c->pieces2; q++) {
+                k += launch_spmv(c->S2, g, c->m, c->tmp, c->Av, c->state, c->stream, q);
+                CU(cudaEventRecord(c->ev_piece[q], c->stream));
+                if (c->p2p) {
+                        if (piece_push(c, c->peer_av, c->n_off, c->piece_rows_all2, c->pieces2, q, c->ev_piece[q])) return 1;
+                } else {
+                        CU(cudaStreamWaitEvent(c->comm_stream, c->ev_piece[q], 0));
+                        if (piece_broadcast(c, c->Av_full, c->n_off, c->piece_rows_all2, c->pieces2, q, c->comm_stream)) return 1;
+                }
+        }
+        c->launches += k;
+        if (tm) tm->end(c, k);
+
+        // dots on the local rows do not need the remote part of Av: they overlap the tail of the exchange
+        if (tm) tm->begin(c, BLK_PH_DOTS);
+        k = launch_dots(g, c->m, lrows, vloc, c->Av, c->sums, c->dots_blocks, c->state, SmallFuse(), c->stream);
+        c->launches += k;
+        if (tm) tm->end(c, k);
+        if (tm) tm->begin(c, BLK_PH_EXCHANGE);
+        if (c->p2p) {
+                // my pushes are done when the copy stream drains; the all-reduce below completes only
+                // after every rank has reached it, i.e. after every rank's pushes have landed
+                if (pushes_done(c)) return 1;
+        } else {
+                CU(cudaEventRecord(c->ev_comm, c->comm_stream));
+                CU(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
+        }
+        NC(g_nccl.AllReduce(c->sums, c->sums, (size_t)2 * np * np, ncclUint64, ncclSum, c->comm, c->stream));
+        if (tm) tm->end(c, 0);
+        if (tm) tm->begin(c, BLK_PH_SMALL);
+        k = launch_small(g, c->m, c->sums, c->mats, c->state, 0, c->stream);
+        c->launches += k;
+        if (tm) tm->end(c, k);
+        if (tm) tm->begin(c, BLK_PH_ORTHO);
+        k = launch_ortho(g, c->m, lrows, vloc, c->Av, c->p, vloc, c->p, c->mats, c->state, 0, c->stream);
+        c->launches += k;
+        if (tm) tm->end(c, k);
+
+        // tmp <- S1 v' through the recurrence: U = S1 Av (never skipped: the limit may just have been
+        // reached), then orthogonalize(tmp, U, Tp) on the finished rows (skipped exactly when the real
+        // orthogonalize is), then broadcast
+        if (c->tmp_prev)
+                CU(cudaMemcpyAsync(c->tmp_prev, tloc, sizeof(u32) * (size_t)(c->m1() - c->m0()) * np,
+                                   cudaMemcpyDeviceToDevice, c->stream));
+        if (tm) tm->begin(c, BLK_PH_SPMV1);
+        k = 0;
+        for (int q = 0; q < c->pieces; q++) {
+                k += launch_spmv(c->S1, g, c->m, c->Av_full, c->U, nullptr, c->stream, q);
+                int64_t lo = c->S1.piece_row[q], hi = c->S1.piece_row[q + 1];
+                if (hi > lo)
+                        k += launch_ortho(g, c->m, hi - lo, tloc + (size_t)lo * np, c->U + (size_t)lo * np, c->Tp + (size_t)lo * np,
+                                          tloc + (size_t)lo * np, c->Tp + (size_t)lo * np, c->mats, c->state, 0, c->stream);
+                CU(cudaEventRecord(c->ev_piece[q], c->stream));
+                if (c->p2p) {
+                        if (piece_push(c, c->peer_tmp, c->m_off, c->piece_rows_all, c->pieces, q, c->ev_piece[q])) return 1;
+                } else {
+                        CU(cudaStreamWaitEvent(c->comm_stream, c->ev_piece[q], 0));
+                        if (piece_broadcast(c, c->tmp, c->m_off, c->piece_rows_all, c->pieces, q, c->comm_stream)) return 1;
+                }
+        }
+        c->launches += k;
+        if (tm) tm->end(c, k);
+        if (tm) tm->begin(c, BLK_PH_EXCHANGE);
+        if (c->p2p) {
+                if (pushes_done(c)) return 1;
+                NC(g_nccl.AllReduce(c->barrier_word, c->barrier_word, 1, ncclUint64, ncclSum, c->comm, c->stream));   // barrier
+        } else {
+                CU(cudaEventRecord(c->ev_comm, c->comm_stream));
+                CU(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
+        }
+        if (tm) tm->end(c, 0);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(e));
+        return 0;
+}
+
+// establish the invariant of enqueue_iteration_mg from v (full, on every rank) and p_full (may be null)
+int mg_prepare(blk_ctx *c, const u32 *p_full_dev)
+{
+        const int np = c->geo.np;
+        u32 *tloc = c->tmp + (size_t)c->m0() * np;
+        c->launches += launch_spmv(c->S1, c->geo, c->m, c->v, tloc, nullptr, c->stream);
+        if (allgather_rows(c, c->tmp, c->m_off)) return 1;
+        int64_t lm = c->m1() - c->m0();
+        if (p_full_dev) c->launches += launch_spmv(c->S1, c->geo, c->m, p_full_dev, c->Tp, nullptr, c->stream);
+        else CU(cudaMemsetAsync(c->Tp, 0, sizeof(u32) * (size_t)(lm > 0 ? lm : 1) * np, c->stream));
+        if (c->tmp_prev) CU(cudaMemsetAsync(c->tmp_prev, 0, sizeof(u32) * (size_t)(lm > 0 ? lm : 1) * np, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        return 0;
+}
+
 // one iteration of the loop body, sequential/lanczos_modp.c:635-656
 int enqueue_iteration(blk_ctx *c, EventTimer *tm)
 {
+        if (c->mg_recur) return enqueue_iteration_mg(c, tm);
         const Geometry &g = c->geo;
         const int np = g.np;
         int k;
@@ -280,14 +447,7 @@ int enqueue_iteration(blk_ctx *c, EventTimer *tm)
                         k += launch_spmv(c->S1, g, c->m, c->v, c->tmp + (size_t)c->m0() * np, c->state, c->stream, q);
                         CU(cudaEventRecord(c->ev_piece[q], c->stream));
                         CU(cudaStreamWaitEvent(c->comm_stream, c->ev_piece[q], 0));
-                        NC(g_nccl.GroupStart());
-                        for (int r = 0; r < c->world; r++) {
-                                int64_t lo = c->piece_rows_all[(size_t)r * (K + 1) + q], hi = c->piece_rows_all[(size_t)r * (K + 1) + q + 1];
-                                size_t cnt = (size_t)(hi - lo) * np;
-                                u32 *ptr = c->tmp + (size_t)(c->m_off[r] + lo) * np;
-                                if (cnt) NC(g_nccl.Broadcast(ptr, ptr, cnt, ncclUint32, r, c->comm, c->comm_stream));
-                        }
-                        NC(g_nccl.GroupEnd());
+                        if (piece_broadcast(c, c->tmp, c->m_off, c->piece_rows_all, K, q, c->comm_stream)) return 1;
                 }
                 c->launches += k;
                 if (tm) tm->end(c, k);
@@ -470,10 +630,20 @@ int blk_destroy(blk_ctx *c)
         if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
         free_operator(&c->S1);
         free_operator(&c->S2);
-        cudaFree(c->v); cudaFree(c->tmp); cudaFree(c->Av); cudaFree(c->p);
+        cudaFree(c->v); cudaFree(c->tmp); cudaFree(c->p);
+        if (c->Av_full) cudaFree(c->Av_full); else cudaFree(c->Av);
+        cudaFree(c->Tp); cudaFree(c->U); cudaFree(c->tmp_prev);
         cudaFree(c->mats); cudaFree(c->sums); cudaFree(c->state); cudaFree(c->dots_counter);
         cudaFree(c->n_old2new); cudaFree(c->n_new2old);
         if (c->h_state) cudaFreeHost(c->h_state);
+        for (int r = 0; r < (int)c->peer_tmp.size(); r++) {
+                if (r == c->rank) continue;
+                if (c->peer_tmp[r]) cudaIpcCloseMemHandle(c->peer_tmp[r]);
+                if (c->peer_av[r]) cudaIpcCloseMemHandle(c->peer_av[r]);
+        }
+        for (auto e : c->ev_copies) cudaEventDestroy(e);
+        for (auto st : c->copy_streams) cudaStreamDestroy(st);
+        cudaFree(c->barrier_word);
         for (auto e : c->ev_piece) cudaEventDestroy(e);
         if (c->ev_comm) cudaEventDestroy(c->ev_comm);
         if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
@@ -591,7 +761,10 @@ int blk_create(blk_ctx **out, const blk_params *prm)
         int want_pieces = 1;
         if (world > 1) {
                 const char *e = getenv("BLK_PIECES");
-                want_pieces = e ? atoi(e) : 8;
+                // a piece should be worth >= ~0.5 ms of product time (about 25M entries); <= 4 pieces
+                // (8 x B200, config 4: 4 pieces 61.7 it/s, 8 pieces 58.1 it/s)
+                long long per_rank = (long long)(nnz / world);
+                want_pieces = e ? atoi(e) : (int)std::max(1ll, std::min(4ll, per_rank / 25000000ll));
                 if (want_pieces < 1) want_pieces = 1;
                 if (want_pieces > 32) want_pieces = 32;
         }
@@ -633,7 +806,7 @@ int blk_create(blk_ctx **out, const blk_params *prm)
                         cudaFree(cnt);
                         if ((int64_t)hcnt != sel) err = "shard selection count mismatch";
                         else err = build_operator(op, c->geo, prm->chunk_len, hi - lo, cols, lo, sel, sr, sc, sx, m.p, nullptr, nullptr,
-                                                       which ? 1 : want_pieces, c->stream);
+                                                       want_pieces, c->stream);
                         cudaFree(sr); cudaFree(sc); cudaFree(sx);
                 }
                 if (!err.empty()) { free_coo(); fail(err); blk_destroy(c); return 1; }
@@ -681,13 +854,14 @@ int blk_create(blk_ctx **out, const blk_params *prm)
                 }
                 const char *e = getenv("BLK_ALLGATHER");
                 if (!(e && e[0] == 'b')) c->nccl_allgather = g_nccl.AllGather;     // BLK_ALLGATHER=bcast forces broadcasts
-                // every rank needs every rank's piece boundaries of S1 (number of pieces = the minimum)
-                {
+                // every rank needs every rank's piece boundaries of both operators
+                for (int which = 0; which < 2; which++) {
+                        const SpOp &op = which ? c->S2 : c->S1;
                         const int KMAX = 32;
                         std::vector<long long> mine(KMAX + 2, 0), all((size_t)(KMAX + 2) * world, 0);
-                        int K = (int)c->S1.piece_tile.size() - 1;
+                        int K = (int)op.piece_tile.size() - 1;
                         mine[0] = K;
-                        for (int k = 0; k <= K; k++) mine[1 + k] = c->S1.piece_row[k];
+                        for (int k = 0; k <= K; k++) mine[1 + k] = op.piece_row[k];
                         long long *dbuf = nullptr;
                         CUX(cudaMalloc(&dbuf, sizeof(long long) * all.size()));
                         CUX(cudaMemcpyAsync(dbuf + (size_t)c->rank * (KMAX + 2), mine.data(), sizeof(long long) * (KMAX + 2),
@@ -700,20 +874,93 @@ int blk_create(blk_ctx **out, const blk_params *prm)
                         cudaFree(dbuf);
                         bool same = true;
                         for (int r = 0; r < world; r++) same = same && all[(size_t)r * (KMAX + 2)] == K;
-                        c->pieces = same ? K : 1;            // all ranks must agree on the schedule
-                        if (c->pieces > 1) {
-                                c->piece_rows_all.assign((size_t)world * (K + 1), 0);
+                        std::vector<int64_t> &dst = which ? c->piece_rows_all2 : c->piece_rows_all;
+                        int &Kd = which ? c->pieces2 : c->pieces;
+                        if (same) {
+                                Kd = K;
+                                dst.assign((size_t)world * (K + 1), 0);
                                 for (int r = 0; r < world; r++)
                                         for (int k = 0; k <= K; k++)
-                                                c->piece_rows_all[(size_t)r * (K + 1) + k] = all[(size_t)r * (KMAX + 2) + 1 + k];
-                                // highest priority: the block scheduler then places NCCL's few large CTAs ahead
-                                // of the thousands of queued SpMV blocks instead of after them
-                                int pr_least = 0, pr_greatest = 0;
-                                CUX(cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest));
-                                CUX(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, pr_greatest));
-                                c->ev_piece.resize(K);
-                                for (auto &ev : c->ev_piece) CUX(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-                                CUX(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
+                                                dst[(size_t)r * (K + 1) + k] = all[(size_t)r * (KMAX + 2) + 1 + k];
+                        } else {                       // ranks disagree (tiny operators): one piece = the whole block
+                                Kd = 1;
+                                dst.assign((size_t)world * 2, 0);
+                                const std::vector<int64_t> &off = which ? c->n_off : c->m_off;
+                                for (int r = 0; r < world; r++) dst[(size_t)r * 2 + 1] = off[r + 1] - off[r];
+                        }
+                }
+                {
+                        // highest priority: the block scheduler then places NCCL's few large CTAs ahead
+                        // of the thousands of queued SpMV blocks instead of after them
+                        int pr_least = 0, pr_greatest = 0;
+                        CUX(cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest));
+                        CUX(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, pr_greatest));
+                        c->ev_piece.resize(std::max(c->pieces, c->pieces2));
+                        for (auto &ev : c->ev_piece) CUX(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                        CUX(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
+                }
+                const char *er = getenv("BLK_RECUR");
+                if (!(er && er[0] == '0')) {
+                        c->mg_recur = true;
+                        int64_t lm = c->m1() - c->m0();
+                        size_t bav = sizeof(u32) * (size_t)gather_cap(c->n_off) * np;
+                        size_t blm = sizeof(u32) * (size_t)(lm > 0 ? lm : 1) * np;
+                        CUX(cudaMalloc(&c->Av_full, bav));
+                        CUX(cudaMemsetAsync(c->Av_full, 0, bav, c->stream));
+                        cudaFree(c->Av);
+                        c->Av = c->Av_full + (size_t)c->n0() * np;
+                        CUX(cudaMalloc(&c->Tp, blm)); CUX(cudaMalloc(&c->U, blm));
+                        CUX(cudaMemsetAsync(c->Tp, 0, blm, c->stream));
+                        CUX(cudaMemsetAsync(c->U, 0, blm, c->stream));
+                        if (c->Mc > c->N) { CUX(cudaMalloc(&c->tmp_prev, blm)); CUX(cudaMemsetAsync(c->tmp_prev, 0, blm, c->stream)); }
+                        c->block_bytes += bav + 3 * blm;
+                        CUX(cudaStreamSynchronize(c->stream));
+                        // ---- one-sided pushes over NVLink: exchange IPC handles of tmp and Av_full
+                        // (measured on 8 x B200, config 4: NCCL broadcasts of 4 pieces 61.7 it/s, copy-engine
+                        // pushes 57.9 it/s -- so the pushes are opt-in: BLK_P2P=1)
+                        const char *ep = getenv("BLK_P2P");
+                        if (ep && ep[0] == '1') {
+                                struct Handles { cudaIpcMemHandle_t tmp, av; };
+                                static_assert(sizeof(Handles) == 128, "ipc handle size");
+                                Handles mine;
+                                bool ok = cudaIpcGetMemHandle(&mine.tmp, c->tmp) == cudaSuccess &&
+                                          cudaIpcGetMemHandle(&mine.av, c->Av_full) == cudaSuccess;
+                                unsigned char *dh = nullptr;
+                                CUX(cudaMalloc(&dh, sizeof(Handles) * world));
+                                CUX(cudaMemcpyAsync(dh + sizeof(Handles) * c->rank, &mine, sizeof(Handles), cudaMemcpyHostToDevice, c->stream));
+                                ncclResult_t r3 = g_nccl.AllGather(dh + sizeof(Handles) * c->rank, dh, sizeof(Handles), ncclUint8, c->comm, c->stream);
+                                std::vector<Handles> all(world);
+                                CUX(cudaMemcpyAsync(all.data(), dh, sizeof(Handles) * world, cudaMemcpyDeviceToHost, c->stream));
+                                CUX(cudaStreamSynchronize(c->stream));
+                                cudaFree(dh);
+                                ok = ok && r3 == ncclSuccess;
+                                c->peer_tmp.assign(world, nullptr); c->peer_av.assign(world, nullptr);
+                                c->peer_tmp[c->rank] = c->tmp; c->peer_av[c->rank] = c->Av_full;
+                                for (int r = 0; r < world && ok; r++) {
+                                        if (r == c->rank) continue;
+                                        void *a = nullptr, *b = nullptr;
+                                        ok = cudaIpcOpenMemHandle(&a, all[r].tmp, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess &&
+                                             cudaIpcOpenMemHandle(&b, all[r].av, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+                                        c->peer_tmp[r] = (u32 *)a; c->peer_av[r] = (u32 *)b;
+                                }
+                                cudaGetLastError();            // a failed open must not poison later calls
+                                // every rank must take the same path: agree through a sum
+                                unsigned long long *flag = nullptr, hflag = ok ? 1ull : 0ull;
+                                CUX(cudaMalloc(&flag, sizeof(unsigned long long)));
+                                CUX(cudaMemcpyAsync(flag, &hflag, sizeof(hflag), cudaMemcpyHostToDevice, c->stream));
+                                NC(g_nccl.AllReduce(flag, flag, 1, ncclUint64, ncclSum, c->comm, c->stream));
+                                CUX(cudaMemcpyAsync(&hflag, flag, sizeof(hflag), cudaMemcpyDeviceToHost, c->stream));
+                                CUX(cudaStreamSynchronize(c->stream));
+                                cudaFree(flag);
+                                c->p2p = hflag == (unsigned long long)world;
+                                if (c->p2p) {
+                                        c->copy_streams.resize(world - 1); c->ev_copies.resize(world - 1);
+                                        for (auto &st : c->copy_streams) CUX(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+                                        for (auto &ev : c->ev_copies) CUX(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                                        CUX(cudaMalloc(&c->barrier_word, sizeof(u64)));
+                                        CUX(cudaMemsetAsync(c->barrier_word, 0, sizeof(u64), c->stream));
+                                        CUX(cudaStreamSynchronize(c->stream));
+                                }
                         }
                 }
         }
@@ -736,7 +983,20 @@ int blk_set_state(blk_ctx *c, const uint32_t *v, const uint32_t *p, int32_t n_it
                 CU(cudaMemsetAsync(c->p, 0, sizeof(u32) * (size_t)(ln > 0 ? ln : 1) * np, c->stream));
         }
         CU(cudaMemsetAsync(c->tmp, 0, sizeof(u32) * (size_t)c->Mc * np, c->stream));
-        CU(cudaMemsetAsync(c->Av, 0, sizeof(u32) * (size_t)(ln > 0 ? ln : 1) * np, c->stream));
+        if (c->Av_full) CU(cudaMemsetAsync(c->Av_full, 0, sizeof(u32) * (size_t)gather_cap(c->n_off) * np, c->stream));
+        else CU(cudaMemsetAsync(c->Av, 0, sizeof(u32) * (size_t)(ln > 0 ? ln : 1) * np, c->stream));
+        if (c->mg_recur) {
+                // invariant of the multi-GPU loop: tmp = S1 v (gathered), Tp = S1 p (local rows)
+                u32 *pfull = nullptr;
+                if (p) {
+                        CU(cudaMalloc(&pfull, sizeof(u32) * (size_t)c->N * np));
+                        if (upload_rows(c, pfull, p, c->N)) { cudaFree(pfull); return 1; }
+                }
+                int rc = mg_prepare(c, pfull);
+                cudaFree(pfull);
+                if (rc) return 1;
+        }
+        c->ran_since_set = false;
         c->iters = n_iterations; c->stopped = 0;
         c->tmp_is_spmv = false; c->any_ortho = n_iterations > 0;
         memset(c->h_state, 0, sizeof(DevSmall));
@@ -788,6 +1048,7 @@ int blk_iterate(blk_ctx *c, int32_t max_iters, int32_t *iters_total, int32_t *st
                 if (c->stopped) c->tmp_is_spmv = true;
                 else if (c->iters > before) c->tmp_is_spmv = false;
                 if (c->iters > before) c->any_ortho = true;
+                c->ran_since_set = true;
         }
         if (iters_total) *iters_total = c->iters;
         if (stopped) *stopped = c->stopped;
@@ -820,7 +1081,22 @@ int blk_get_state(blk_ctx *c, uint32_t *v, uint32_t *tmp, uint32_t *Av, uint32_t
                 // orthogonalize + copy (:652-656) and S1*v in rows [0,Mc) after the first product (:635)
                 memset(tmp, 0, sizeof(u32) * (size_t)pad);
                 std::vector<u32> ht((size_t)Mc * n);
-                if (download_rows(c, ht.data(), c->tmp, Mc)) return 1;
+                if (c->mg_recur && !c->ran_since_set) {
+                        // nothing has run since blk_set_state: the reference's tmp is still all zero there
+                        // (the device already holds S1*v for the first iteration)
+                        std::fill(ht.begin(), ht.end(), 0u);
+                } else if (c->mg_recur && !c->tmp_is_spmv && Mc > N) {
+                        // the device tmp already belongs to the NEXT iteration; the reference still shows
+                        // the previous product in rows [N,Mc): gather the saved copy
+                        u32 *full = nullptr;
+                        CU(cudaMalloc(&full, sizeof(u32) * (size_t)gather_cap(c->m_off) * np));
+                        CU(cudaMemcpyAsync(full + (size_t)c->m0() * np, c->tmp_prev, sizeof(u32) * (size_t)(c->m1() - c->m0()) * np,
+                                           cudaMemcpyDeviceToDevice, c->stream));
+                        if (allgather_rows(c, full, c->m_off)) { cudaFree(full); return 1; }
+                        int rc = download_rows(c, ht.data(), full, Mc);
+                        cudaFree(full);
+                        if (rc) return 1;
+                } else if (download_rows(c, ht.data(), c->tmp, Mc)) return 1;
                 if (c->tmp_is_spmv) {
                         if (c->any_ortho && N > Mc)
                                 memcpy(tmp + (size_t)Mc * n, vsrc + (size_t)Mc * n, sizeof(u32) * (size_t)(N - Mc) * n);

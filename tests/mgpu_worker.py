@@ -23,6 +23,8 @@ def main():
         (B.synth.powerlaw_rows(3000, 2700, mean=9, seed=3, with_empty_rows=11), 4, 65537, False, 9),
         (B.synth.uniform_nnz(2500, 3100, 30000, seed=4, order="col"), 8, 2147483647, True, 7),
         (B.synth.powerlaw_rows(1500, 1400, mean=6, seed=5), 3, 1073741789, False, -1),      # run to the end
+        (B.synth.powerlaw_rows(1200, 1500, mean=7, seed=6), 4, 65537, False, 6),             # Mc > N: tmp keeps old rows
+        (B.synth.uniform_nnz(40000, 52000, 600000, seed=7, order="col"), 16, 2147483647, True, 5),   # many tiles: 8 pieces
     ]
     for ci, (M, n, p, right, stop_after) in enumerate(cases):
         Mp = M.reduced(p)
