@@ -88,3 +88,39 @@ def test_two_rank_gloo_exchange_reproduces_sequential(lib):
     for pr in procs:
         pr.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_tmp_recurrence_identity(lib):
+    """The multi-GPU loop never gathers the new v: it obtains S1 v' as orthogonalize(S1 v, S1 Av, S1 p)
+    (context.cu, enqueue_iteration_mg).  Check that identity, bit for bit, with the CPU oracle."""
+    from oracle.oracle import Oracle
+    O = Oracle()
+    for (p, n, right) in ((2147483647, 4, False), (65537, 3, True), (1073741789, 8, False)):
+        M = lib.synth.powerlaw_rows(500, 620, mean=6, seed=n, with_empty_rows=4).reduced(p)
+        N = M.ncols if right else M.nrows
+        Mc = M.nrows if right else M.ncols
+        v = O.start_block(N * n, p)
+        pb = np.zeros(N * n, np.uint32)
+        T = O.sparse_matrix_vector_product(M, v, not right, n, p)          # S1 v
+        Tp = np.zeros(Mc * n, np.uint32)                                      # S1 p
+        for it in range(5):
+            Av = O.sparse_matrix_vector_product(M, T, right, n, p)
+            a, b = O.block_dot_products(N, Av, v, n, p)
+            npiv, winv, d = O.semi_inverse(a, n, p)
+            assert npiv > 0
+            v2, p2 = O.orthogonalize(v, pb, d, a, b, winv, N, Av, n, p)
+            U = O.sparse_matrix_vector_product(M, Av, not right, n, p)      # S1 Av
+            T2, Tp2 = O.orthogonalize(T, Tp, d, a, b, winv, Mc, U, n, p)     # the recurrence
+            assert np.array_equal(T2, O.sparse_matrix_vector_product(M, v2, not right, n, p))
+            assert np.array_equal(Tp2, O.sparse_matrix_vector_product(M, p2, not right, n, p))
+            v, pb, T, Tp = v2, p2, T2, Tp2
+        # linearity holds for ANY n x n factors and selection mask (rank-deficient iterations): random ones
+        rng = np.random.default_rng(p % 1000)
+        d = rng.integers(0, 2, size=n).astype(np.uint32)
+        a, b, winv = (rng.integers(0, p, size=n * n).astype(np.uint32) for _ in range(3))
+        Av = O.sparse_matrix_vector_product(M, T, right, n, p)
+        v2, p2 = O.orthogonalize(v, pb, d, a, b, winv, N, Av, n, p)
+        U = O.sparse_matrix_vector_product(M, Av, not right, n, p)
+        T2, Tp2 = O.orthogonalize(T, Tp, d, a, b, winv, Mc, U, n, p)
+        assert np.array_equal(T2, O.sparse_matrix_vector_product(M, v2, not right, n, p))
+        assert np.array_equal(Tp2, O.sparse_matrix_vector_product(M, p2, not right, n, p))
