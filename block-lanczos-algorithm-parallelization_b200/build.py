@@ -53,7 +53,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
 
 def build_driver(force: bool = False) -> str:
-    srcs = [os.path.join(DRIVER_DIR, f) for f in ("lanczos_modp.c", "mtx_io.c")]
+    srcs = [os.path.join(DRIVER_DIR, f) for f in ("lanczos_modp_gpu.c", "mtx_io.c")]
     if not all(os.path.exists(s) for s in srcs):
         raise FileNotFoundError("driver sources missing")
     build_library()
@@ -66,6 +66,6 @@ def build_driver(force: bool = False) -> str:
 
 if __name__ == "__main__":
     build_library(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    if os.path.exists(os.path.join(DRIVER_DIR, "lanczos_modp.c")):
+    if os.path.exists(os.path.join(DRIVER_DIR, "lanczos_modp_gpu.c")):
         build_driver(force="--force" in sys.argv)
     print(LIB)
