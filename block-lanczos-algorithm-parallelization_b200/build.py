@@ -60,7 +60,7 @@ def build_driver(force: bool = False) -> str:
     if force or _stale(DRIVER, srcs + [LIB, os.path.join(DRIVER_DIR, "mtx_io.h")]):
         subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-O2", "-Wall", "-Wextra", "-Werror",
                                "-I", os.path.join(ROOT, "include"), *srcs, "-o", DRIVER,
-                               "-L", PKG, "-lblklanczos", "-Wl,-rpath,$ORIGIN/..", "-lm"])
+                               "-L", PKG, "-lblklanczos", "-Wl,-rpath,$ORIGIN/..", "-lm", "-lpthread"])
     return DRIVER
 
 

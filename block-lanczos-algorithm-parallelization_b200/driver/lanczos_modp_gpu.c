@@ -23,6 +23,7 @@
 #include <err.h>
 #include <getopt.h>
 #include <inttypes.h>
+#include <pthread.h>
 #include <stdbool.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -194,24 +195,65 @@ static void report(struct progress *pg, int n_iterations)
                         errx(1, "%s", blk_last_error());                                           \
         } while (0)
 
-static void write_checkpoint(blk_ctx *ctx, long pad, int n_iterations, const struct progress *pg,
-                             uint32_t *v, uint32_t *tmp, uint32_t *Av, uint32_t *p)
+/* Checkpoints (openMP/lanczos_modp.c:1013-1022): the four blocks come back from the GPU in one
+ * synchronous blk_get_state into a private set of host buffers; formatting and writing the text
+ * files (the slow part: 4 * block_size_pad lines) then runs on a writer thread while the GPU
+ * already iterates again.  A new snapshot (or program exit) first joins the previous writer. */
+struct snapshot {
+        long pad;
+        int n_iterations;
+        double t_start, t_now;
+        uint32_t *blk[4];
+        pthread_t thread;
+        bool running;
+};
+
+static void *snapshot_writer(void *arg)
 {
-        GPU(blk_get_state(ctx, v, tmp, Av, p));
-        printf("\n");
+        struct snapshot *s = arg;
         /* verbosity.txt: n_iterations, start, now (openMP/lanczos_modp.c:591-609) */
         FILE *f = fopen("verbosity.txt.tmp", "w");
         if (!f)
                 err(1, "cannot open %s", "verbosity.txt");
         printf("\t\t>> Saving verbosity engine infos in %s\n", "verbosity.txt");
-        fprintf(f, "%d\n%f\n%f\n", n_iterations, pg->start - pg->extra, wall());
+        fprintf(f, "%d\n%f\n%f\n", s->n_iterations, s->t_start, s->t_now);
         fclose(f);
         if (rename("verbosity.txt.tmp", "verbosity.txt") != 0)
                 err(1, "cannot write verbosity.txt");
-        vector_save("v.txt", pad, v);
-        vector_save("tmp.txt", pad, tmp);
-        vector_save("Av.txt", pad, Av);
-        vector_save("p.txt", pad, p);
+        static const char *names[4] = {"v.txt", "tmp.txt", "Av.txt", "p.txt"};
+        for (int k = 0; k < 4; k++)
+                vector_save(names[k], s->pad, s->blk[k]);
+        return NULL;
+}
+
+static void snapshot_join(struct snapshot *s)
+{
+        if (s->running) {
+                pthread_join(s->thread, NULL);
+                s->running = false;
+        }
+}
+
+static void write_checkpoint(blk_ctx *ctx, struct snapshot *s, long pad, int n_iterations, const struct progress *pg)
+{
+        snapshot_join(s);
+        if (!s->blk[0]) {
+                for (int k = 0; k < 4; k++) {
+                        s->blk[k] = malloc(sizeof(uint32_t) * (size_t)pad);
+                        if (!s->blk[k])
+                                errx(1, "impossible d'allouer les blocs de vecteur");
+                }
+        }
+        GPU(blk_get_state(ctx, s->blk[0], s->blk[1], s->blk[2], s->blk[3]));
+        printf("\n");
+        s->pad = pad;
+        s->n_iterations = n_iterations;
+        s->t_start = pg->start - pg->extra;
+        s->t_now = wall();
+        if (pthread_create(&s->thread, NULL, snapshot_writer, s) != 0)
+                snapshot_writer(s);                      /* no thread: write synchronously */
+        else
+                s->running = true;
 }
 
 static int read_checkpoint_info(double *extra)
@@ -285,6 +327,8 @@ int main(int argc, char **argv)
         printf("  - Main loop\n");
         pg.start = wall();
         double last_checkpoint = wall();
+        struct snapshot snap;
+        memset(&snap, 0, sizeof(snap));
         int stopped = 0;
         int batch = 1;
         while (!stopped) {
@@ -309,10 +353,11 @@ int main(int argc, char **argv)
                 report(&pg, n_iterations);
                 if (o.checkpoint && !stopped && n_iterations > before &&
                     wall() - last_checkpoint >= o.checkpoint_every) {
-                        write_checkpoint(ctx, pad, n_iterations, &pg, v, tmp, Av, p);
+                        write_checkpoint(ctx, &snap, pad, n_iterations, &pg);
                         last_checkpoint = wall();
                 }
         }
+        snapshot_join(&snap);
         printf("\n");
 
         GPU(blk_get_state(ctx, v, tmp, NULL, NULL));
