@@ -144,3 +144,24 @@ def read_kernel_block(path: str) -> np.ndarray:
         N, n = (int(t) for t in line.split())
         vals = np.loadtxt(f, dtype=np.int64, ndmin=1)
     return vals.reshape(n, N).T.astype(np.uint32).copy()
+
+
+def reference_start_block(count: int, p: int) -> np.ndarray:
+    """The reference's start block: v[i] = random64() % prime for i row-major over N*n, xoshiro256+
+    with its fixed seed (sequential/lanczos_modp.c:64-87, 624-625).  Host-side mirror of what the C
+    driver does (driver/lanczos_modp_gpu.c); pure Python integers, ~1 us per value."""
+    mask = (1 << 64) - 1
+    s0, s1, s2, s3 = 0x1415926535, 0x8979323846, 0x2643383279, 0x5028841971
+    out = np.empty(count, dtype=np.uint32)
+    for t in range(count):
+        x = (s0 + s3) & mask
+        r = ((((x << 23) | (x >> 41)) & mask) + s0) & mask
+        sh = (s1 << 17) & mask
+        s2 ^= s0
+        s3 ^= s1
+        s1 ^= s2
+        s0 ^= s3
+        s2 ^= sh
+        s3 = ((s3 << 45) | (s3 >> 19)) & mask
+        out[t] = r % p
+    return out

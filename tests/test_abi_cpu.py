@@ -71,3 +71,8 @@ def test_mtx_roundtrip(tmp_path, lib):
     M2 = lib.synth.read_mtx(path)
     assert (M2.nrows, M2.ncols, M2.nnz) == (M.nrows, M.ncols, M.nnz)
     assert np.array_equal(M2.i, M.i) and np.array_equal(M2.j, M.j) and np.array_equal(M2.x, M.x)
+
+
+def test_python_start_block_is_the_references(lib, oracle):
+    for p in (65537, 2147483647, 7):
+        assert np.array_equal(lib.synth.reference_start_block(5000, p), oracle.start_block(5000, p))

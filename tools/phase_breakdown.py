@@ -3,14 +3,12 @@ launches bracketed by CUDA events, so launch gaps are visible too)."""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import blk_lanczos_b200 as B
-from oracle.oracle import Oracle
-O = Oracle()
 for k in (1, 2, 3):
     M, a = B.synth.baseline_config(k)
     p, n, right = a["p"], a["n"], a["right"]
     N = M.ncols if right else M.nrows
     ctx = B.BlockLanczos(M.reduced(p), n=n, prime=p, right=right)
-    v0 = O.start_block(N * n, p)
+    v0 = B.synth.reference_start_block(N * n, p)
     ctx.set_state(v0); ctx.iterate(32)
     ctx.set_profiling(True)
     t0 = time.perf_counter(); it, _ = ctx.iterate(500); dt = time.perf_counter() - t0

@@ -4,9 +4,7 @@ import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import blk_lanczos_b200 as B
-from oracle.oracle import Oracle          # only for the reference's start block (host RNG)
 
-O = Oracle()
 out = []
 for k in (1, 2, 3):
     M, a = B.synth.baseline_config(k)
@@ -15,7 +13,7 @@ for k in (1, 2, 3):
     N = M.ncols if right else M.nrows
     Mc = M.nrows if right else M.ncols
     ctx = B.BlockLanczos(Mp, n=n, prime=p, right=right)
-    v0 = O.start_block(N * n, p)
+    v0 = B.synth.reference_start_block(N * n, p)
     ctx.set_state(v0); ctx.iterate(64)                # warm-up (graph capture, clocks)
     ctx.set_state(v0)
     t0 = time.perf_counter()
