@@ -158,15 +158,18 @@ __device__ __forceinline__ void limb_planes(u32 (&L)[4], u32 x0, u32 x1, u32 x2,
 // step.  The k-slot -> row map is free as long as both operands use it: slot (half h, tig, beta)
 // is row r0 + 16h + 4 beta + tig, so one load instruction (fixed h, beta) touches 4 consecutive
 // rows = 2 full 128-byte lines at n_pad = 16 instead of 4 half-used ones.
-template <int NC>
+template <int NC, bool FULL>
 __device__ __forceinline__ void column_planes(u32 (&lo)[NC][4], u32 (&hi)[NC][4], const u32 *__restrict__ X, int NP,
-                                              int64_t r0, int col, int tig, int64_t rows, bool full)
+                                              int64_t r0, int col, int tig, int64_t rows)
 {
         u32 x[8][NC];
+        // all 8 rows of this thread sit at compile-time offsets from one base pointer; the row-bound
+        // tests exist only in the last (partial) step of the block
+        const u32 *base = X + (r0 + tig) * NP + col;
 #pragma unroll
         for (int q = 0; q < 8; q++) {
-                int64_t r = r0 + (q < 4 ? 0 : 16) + 4 * (q & 3) + tig;
-                if (full || r < rows) load_words<NC>(x[q], X + r * NP + col, true);
+                const int dr = (q < 4 ? 0 : 16) + 4 * (q & 3);
+                if (FULL || r0 + tig + dr < rows) load_words<NC>(x[q], base + (int64_t)dr * NP, true);
                 else {
 #pragma unroll
                         for (int c = 0; c < NC; c++) x[q][c] = 0;
@@ -253,18 +256,22 @@ k_dots_mma(int64_t rows, const u32 *__restrict__ v, const u32 *__restrict__ Av,
         int since = 0;
         for (int64_t step = blockIdx.x; step < nstep; step += gridDim.x) {
                 const int64_t r0 = step * 32;
-                const bool full = r0 + 32 <= rows;
                 // left operands: columns ib*CB + 2g, 2g+1 (CB = 16) or ib*CB + g (CB = 8) of v and Av
                 u32 vlo[NT][4], vhi[NT][4], alo[NT][4], ahi[NT][4], blo[NT][4], bhi[NT][4];
-                column_planes<NT>(vlo, vhi, v, NP, r0, ib * CB + NT * g, tig, rows, full);
-                column_planes<NT>(alo, ahi, Av, NP, r0, ib * CB + NT * g, tig, rows, full);
+                if (r0 + 32 <= rows) {
+                        column_planes<NT, true>(vlo, vhi, v, NP, r0, ib * CB + NT * g, tig, rows);
+                        column_planes<NT, true>(alo, ahi, Av, NP, r0, ib * CB + NT * g, tig, rows);
+                        if (NB > 1) column_planes<NT, true>(blo, bhi, Av, NP, r0, jb * CB + NT * g, tig, rows);
+                } else {
+                        column_planes<NT, false>(vlo, vhi, v, NP, r0, ib * CB + NT * g, tig, rows);
+                        column_planes<NT, false>(alo, ahi, Av, NP, r0, ib * CB + NT * g, tig, rows);
+                        if (NB > 1) column_planes<NT, false>(blo, bhi, Av, NP, r0, jb * CB + NT * g, tig, rows);
+                }
                 if (NB == 1) {
 #pragma unroll
                         for (int c = 0; c < NT; c++)
 #pragma unroll
                                 for (int a = 0; a < 4; a++) { blo[c][a] = alo[c][a]; bhi[c][a] = ahi[c][a]; }
-                } else {
-                        column_planes<NT>(blo, bhi, Av, NP, r0, jb * CB + NT * g, tig, rows, full);
                 }
 #pragma unroll
                 for (int a = 0; a < MT; a++) {
