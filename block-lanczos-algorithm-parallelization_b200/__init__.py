@@ -27,7 +27,8 @@ PHASES = ("spmv1", "spmv2", "dots", "small", "ortho", "exchange")
 # every symbol include/blk_lanczos.h declares
 ABI_SYMBOLS = (
     "blk_abi_version", "blk_last_error", "blk_device_count", "blk_nccl_unique_id", "blk_create",
-    "blk_destroy", "blk_plan_shards", "blk_block_pad", "blk_set_state", "blk_iterate", "blk_get_state", "blk_get_small",
+    "blk_destroy", "blk_plan_shards", "blk_block_pad", "blk_set_state", "blk_iterate", "blk_get_state", "blk_final_check",
+    "blk_check_kernel_block", "blk_get_small",
     "blk_spmv", "blk_block_dot_products", "blk_semi_inverse", "blk_orthogonalize",
     "blk_set_profiling", "blk_get_phase_times", "blk_time_spmv", "blk_kernel_launches", "blk_get_info",
 )
@@ -82,6 +83,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.blk_set_state.argtypes = [vp, vp, vp, i32]
     L.blk_iterate.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
     L.blk_get_state.argtypes = [vp, vp, vp, vp, vp]
+    L.blk_final_check.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
+    L.blk_check_kernel_block.argtypes = [vp, vp, C.POINTER(i32)]
     L.blk_get_small.argtypes = [vp, vp, vp, vp, vp, C.POINTER(i32)]
     L.blk_spmv.argtypes = [vp, vp, vp, i32]
     L.blk_block_dot_products.argtypes = [vp, vp, vp, i64, vp, vp]
@@ -256,6 +259,20 @@ class BlockLanczos:
         self._ck(self.L.blk_get_state(self.h, _ptr(out.get("v")), _ptr(out.get("tmp")),
                                       _ptr(out.get("Av")), _ptr(out.get("p"))))
         return out
+
+    def final_check(self):
+        """(v != 0, M^T v == 0) evaluated on the device; sequential/lanczos_modp.c:560-582."""
+        a, b = C.c_int32(0), C.c_int32(0)
+        self._ck(self.L.blk_final_check(self.h, C.byref(a), C.byref(b)))
+        return bool(a.value), bool(b.value)
+
+    def check_kernel_block(self, x) -> bool:
+        """checker_modp's verdict (checker_modp.c:146-204) for a block of N*n residues."""
+        x = _u32(x)
+        assert x.size >= self.N * self.n
+        ok = C.c_int32(0)
+        self._ck(self.L.blk_check_kernel_block(self.h, _ptr(x), C.byref(ok)))
+        return bool(ok.value)
 
     def get_small(self):
         n = self.n

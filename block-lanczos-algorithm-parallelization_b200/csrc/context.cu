@@ -258,6 +258,48 @@ __global__ void k_select_range(int64_t nnz, const int32_t *__restrict__ key, con
 
 inline unsigned nb(int64_t n) { return (unsigned)((n + 255) / 256); }
 
+// flags[0] |= any element non-zero; flags[1] |= any element >= p
+__global__ void k_scan_block(const u32 *__restrict__ a, int64_t count, u32 p, int *__restrict__ flags)
+{
+        int nz = 0, big = 0;
+        for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x) {
+                u32 x = a[e];
+                nz |= x != 0;
+                big |= x >= p;
+        }
+        if (__any_sync(0xffffffffu, nz) && (threadIdx.x & 31) == 0) atomicOr(&flags[0], 1);
+        if (__any_sync(0xffffffffu, big) && (threadIdx.x & 31) == 0) atomicOr(&flags[1], 1);
+}
+
+// scan `rows` rows (leading dimension np) and return (any non-zero, any >= p), summed over the ranks
+int scan_rows(blk_ctx *c, const u32 *a, int64_t rows, int *any_nonzero, int *any_big)
+{
+        unsigned long long *d = nullptr, h[2] = {0, 0};
+        int *flags = nullptr, hf[2] = {0, 0};
+        CU(cudaMalloc(&flags, 2 * sizeof(int)));
+        CU(cudaMalloc(&d, 2 * sizeof(unsigned long long)));
+        CU(cudaMemsetAsync(flags, 0, 2 * sizeof(int), c->stream));
+        int64_t count = rows * c->geo.np;
+        if (count > 0) {
+                unsigned blocks = (unsigned)std::min<int64_t>(148 * 8, (count + 255) / 256);
+                k_scan_block<<<blocks, 256, 0, c->stream>>>(a, count, c->m.p, flags);
+                c->launches++;
+        }
+        CU(cudaMemcpyAsync(hf, flags, sizeof(hf), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if (c->world > 1) {
+                h[0] = hf[0]; h[1] = hf[1];
+                CU(cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+                NC(g_nccl.AllReduce(d, d, 2, ncclUint64, ncclSum, c->comm, c->stream));
+                CU(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+                CU(cudaStreamSynchronize(c->stream));
+                hf[0] = h[0] != 0; hf[1] = h[1] != 0;
+        }
+        cudaFree(flags); cudaFree(d);
+        *any_nonzero = hf[0]; *any_big = hf[1];
+        return 0;
+}
+
 // buf holds gather_cap(off) rows; every rank contributes rows [off[rank], off[rank+1]) in place
 int allgather_rows(blk_ctx *c, u32 *buf, const std::vector<int64_t> &off)
 {
@@ -1127,6 +1169,57 @@ int blk_get_state(blk_ctx *c, uint32_t *v, uint32_t *tmp, uint32_t *Av, uint32_t
                         if (rc) return 1;
                 }
         }
+        return 0;
+}
+
+int blk_final_check(blk_ctx *c, int32_t *v_nonzero, int32_t *vtm_zero)
+{
+        if (!c || !v_nonzero || !vtm_zero) return fail("blk_final_check: null argument");
+        CU(cudaSetDevice(c->device));
+        const int np = c->geo.np;
+        int nz = 0, big = 0;
+        // v: every rank scans its own rows (padding columns are zero)
+        if (scan_rows(c, c->v + (size_t)c->n0() * np, c->n1() - c->n0(), &nz, &big)) return 1;
+        *v_nonzero = nz;
+        // tmp = S1 v of the current v: already there when the loop stopped on "no pivot" (or, in the
+        // multi-GPU recurrence, whenever the loop has run); otherwise compute it into a scratch block
+        const int64_t lm = c->m1() - c->m0();
+        bool have = c->tmp_is_spmv || (c->mg_recur && c->ran_since_set);
+        const u32 *src = c->tmp + (size_t)c->m0() * np;
+        u32 *scratch = nullptr;
+        if (!have) {
+                if (c->world > 1 && allgather_rows(c, c->v, c->n_off)) return 1;
+                CU(cudaMalloc(&scratch, sizeof(u32) * (size_t)(lm > 0 ? lm : 1) * np));
+                c->launches += launch_spmv(c->S1, c->geo, c->m, c->v, scratch, nullptr, c->stream);
+                src = scratch;
+        }
+        int rc = scan_rows(c, src, lm, &nz, &big);
+        cudaFree(scratch);
+        if (rc) return 1;
+        *vtm_zero = !nz;
+        return 0;
+}
+
+int blk_check_kernel_block(blk_ctx *c, const uint32_t *x, int32_t *ok)
+{
+        if (!c || !x || !ok) return fail("blk_check_kernel_block: null argument");
+        CU(cudaSetDevice(c->device));
+        const int np = c->geo.np;
+        const int64_t lm = c->m1() - c->m0();
+        u32 *dx = nullptr, *dy = nullptr;
+        CU(cudaMalloc(&dx, sizeof(u32) * (size_t)c->N * np));
+        CU(cudaMalloc(&dy, sizeof(u32) * (size_t)(lm > 0 ? lm : 1) * np));
+        int rc = upload_rows(c, dx, x, c->N, c->n_new2old);
+        int nz = 0, big = 0, ynz = 0, ybig = 0;
+        if (!rc) rc = scan_rows(c, dx + (size_t)c->n0() * np, c->n1() - c->n0(), &nz, &big);
+        if (!rc && !big) {
+                // entries >= p are rejected before the product, as in checker_modp.c:150-153
+                c->launches += launch_spmv(c->S1, c->geo, c->m, dx, dy, nullptr, c->stream);
+                rc = scan_rows(c, dy, lm, &ynz, &ybig);
+        }
+        cudaFree(dx); cudaFree(dy);
+        if (rc) return 1;
+        *ok = nz && !big && !ynz;
         return 0;
 }
 

@@ -360,15 +360,12 @@ int main(int argc, char **argv)
         snapshot_join(&snap);
         printf("\n");
 
-        GPU(blk_get_state(ctx, v, tmp, NULL, NULL));
+        GPU(blk_get_state(ctx, v, NULL, NULL, NULL));
         if (o.stop_after < 0) {
-                /* final_check, sequential/lanczos_modp.c:560-582 */
+                /* final_check, sequential/lanczos_modp.c:560-582, evaluated on the device */
+                int32_t nonzero = 0, annihilated = 0;
+                GPU(blk_final_check(ctx, &nonzero, &annihilated));
                 printf("Final check:\n");
-                bool nonzero = false, annihilated = true;
-                for (long t = 0; t < N * n; t++)
-                        nonzero |= (v[t] != 0);
-                for (long t = 0; t < Mc * n; t++)
-                        annihilated &= (tmp[t] == 0);
                 printf(nonzero ? "  - OK:    v != 0\n" : "  - KO:    v == 0\n");
                 printf(annihilated ? "  - OK: vt*M == 0\n" : "  - KO: vt*M != 0\n");
         }

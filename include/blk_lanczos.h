@@ -104,6 +104,14 @@ int  blk_iterate(blk_ctx *ctx, int32_t max_iters, int32_t *iters_total, int32_t 
  * (blk_block_pad u32 each; any pointer may be NULL).  Contents are identical
  * to the reference's v/tmp/Av/p at the same point of the loop.             */
 int  blk_get_state(blk_ctx *ctx, uint32_t *v, uint32_t *tmp, uint32_t *Av, uint32_t *p);
+/* final_check (sequential/lanczos_modp.c:560-582) on the device, without copying the blocks back:
+ * *v_nonzero = (v != 0) over the N rows, *vtm_zero = (tmp == 0) over the Mc rows, where tmp is the
+ * product M^T v (resp. M v) of the current v -- the state the loop is in after it stopped on
+ * "no pivot" (otherwise that product is computed first into a scratch block). */
+int  blk_final_check(blk_ctx *ctx, int32_t *v_nonzero, int32_t *vtm_zero);
+/* The property checker_modp verifies (checker_modp.c:146-204) for a candidate block x of N*n u32:
+ * every entry < prime, x not all zero, and x*M == 0 (M*x == 0 for --right).  *ok = 1 if all hold. */
+int  blk_check_kernel_block(blk_ctx *ctx, const uint32_t *x, int32_t *ok);
 /* n x n results of the last executed iteration (any may be NULL): vtAv, vtAAv,
  * winv are n*n, d is n; *npiv the value semi_inverse returned.            */
 int  blk_get_small(blk_ctx *ctx, uint32_t *vtAv, uint32_t *vtAAv, uint32_t *winv, uint32_t *d,

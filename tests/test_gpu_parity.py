@@ -263,3 +263,31 @@ def test_relabelled_layout_is_invisible(lib, oracle, forced_relabel, n, p):
             ref = oracle.lanczos_run(M, n, p, right)
             assert full["iters"] == ref["iters"] and np.array_equal(full["v"], ref["v"]) and \
                 np.array_equal(full["tmp"], ref["tmp"])
+
+
+def test_device_side_final_check_and_checker(lib, oracle):
+    """blk_final_check / blk_check_kernel_block against final_check (sequential/lanczos_modp.c:560-582)
+    and checker_modp's property (checker_modp.c:146-204) evaluated with the oracle."""
+    p, n, right = P_MERSENNE, 4, False
+    M = lib.synth.uniform_rows(420, 400, 6, seed=51).reduced(p)
+    N, Mc = M.nrows, M.ncols
+    v0 = oracle.start_block(N * n, p)
+    with lib.BlockLanczos(M, n=n, prime=p, right=right) as ctx:
+        st = ctx.block_lanczos(v0, stop_after=5)
+        # mid-run: v != 0, and M^T v != 0 (computed into a scratch block, state untouched)
+        assert ctx.final_check() == (True, False)
+        again = ctx.get_state()
+        for k in ("v", "tmp", "Av", "p"):
+            assert np.array_equal(again[k], st[k]), k
+        st = ctx.block_lanczos(v0)
+        assert st["stopped"]
+        want = (bool(st["v"].any()), not st["tmp"][:Mc * n].any())
+        assert ctx.final_check() == want == (True, True)
+        V = st["v"][:N * n].copy()
+        assert ctx.check_kernel_block(V)
+        bad = V.copy(); bad[7] = (int(bad[7]) + 1) % p
+        assert not ctx.check_kernel_block(bad)                      # no longer in the kernel
+        assert not ctx.check_kernel_block(np.zeros_like(V))         # all zero is rejected
+        big = V.copy(); big[3] = p                                  # entry >= p is rejected
+        assert not ctx.check_kernel_block(big)
+        assert not oracle.sparse_matrix_vector_product(M, V, True, n, p).any()
