@@ -47,6 +47,11 @@ def main():
         assert got["iters"] == want["iters"] and got["stopped"] == want["stopped"], (ci, got["iters"], want["iters"])
         for k in ("v", "tmp", "Av", "p"):
             assert np.array_equal(got[k], want[k]), ("loop", ci, k, rank)
+        Mc = M.nrows if right else M.ncols
+        fc = ctx.final_check()                      # device-side final_check, reduced over the ranks
+        assert fc == (bool(want["v"].any()), not O.sparse_matrix_vector_product(Mp, want["v"], not right, n, p).any()), (ci, fc)
+        if want["stopped"]:
+            assert ctx.check_kernel_block(want["v"][:N * n]) and not ctx.check_kernel_block(v0)
         ctx.close()
         dist.barrier()
     if rank == 0:
