@@ -136,6 +136,9 @@ static int pick_chunk_len(int64_t stored, int G)
 {
         // aim for >= 8 warps on each of the 148 SMs; cap the chunk so that u64 accumulators never
         // chain more than 64 products (modp.cuh)
+        // (config 4, n = 16: Q = 64 14.57 it/s, 32 14.42, 16 13.94 -- longer chunks mean fewer tile
+        // borders to stitch; small operators need short chunks to fill the SMs)
+        if (stored / ((int64_t)G * 64) >= 148 * 32) return 64;
         int Q = 32;
         while (Q > 8 && stored / ((int64_t)G * Q) < 148 * 8) Q >>= 1;
         return Q;
