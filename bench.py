@@ -290,13 +290,17 @@ def main():
         barrier()
         t0 = time.perf_counter()
         ctx.set_state(v_np)                                   # H2D of the start block (pinned)
+        t1 = time.perf_counter()
         for _ in range(a.steps):
             ctx.iterate(1)                                    # returns (n_iterations, stopped) to the host
+        t2 = time.perf_counter()
         ctx.L.blk_get_state(ctx.h, out_np.ctypes.data, None, None, None)     # D2H of v
         barrier()
-        dt = max_over_ranks(time.perf_counter() - t0)
+        t3 = time.perf_counter()
+        dt = max_over_ranks(t3 - t0)
         e2e = {"value": a.steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": int(N * n * 4 / a.steps + 32), "d2h_bytes_per_step": int(ctx.pad * 4 / a.steps + 32),
+               "seconds": {"set_state": t1 - t0, "iterate": t2 - t1, "get_state": t3 - t2},
                "note": "blk_set_state + K x blk_iterate(1) + blk_get_state(v); state copies amortised over K"}
 
     # -------- roofline of the SpMV kernel (both products), SURVEY 8(d) algorithmic bytes
