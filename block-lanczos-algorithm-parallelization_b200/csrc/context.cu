@@ -1405,6 +1405,10 @@ int blk_time_spmv(blk_ctx *c, int32_t transpose, int32_t reps, double *ms_avg)
         SpOp *op = op_for(c, transpose, &s1);
         const u32 *x = s1 ? c->v : c->tmp;
         u32 *y = s1 ? c->tmp + (size_t)c->m0() * np : c->Av;
+        if (c->mg_recur && s1) {          // keep the loop invariant (tmp = S1 v): time S1 on Av into the scratch block
+                x = c->Av_full;
+                y = c->U;
+        }
         cudaEvent_t a, b;
         CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
         c->launches += launch_spmv(*op, c->geo, c->m, x, y, nullptr, c->stream);    // warm-up
@@ -1416,7 +1420,7 @@ int blk_time_spmv(blk_ctx *c, int32_t transpose, int32_t reps, double *ms_avg)
         CU(cudaEventElapsedTime(&ms, a, b));
         cudaEventDestroy(a); cudaEventDestroy(b);
         *ms_avg = (double)ms / reps;
-        c->tmp_is_spmv = false;
+        if (!c->mg_recur) c->tmp_is_spmv = false;
         return 0;
 }
 
