@@ -33,6 +33,10 @@ CLI_CASES = [
     ("cli_right_n8_mersenne", lambda: synth.uniform_nnz(300, 390, 2600, seed=5, order="col"), 2147483647, 8, True),
     ("cli_left_n3_p1073741789", lambda: synth.powerlaw_rows(240, 200, mean=6, seed=7, with_empty_rows=4), 1073741789, 3, False),
     ("cli_left_n16_mersenne", lambda: synth.powerlaw_rows(420, 400, mean=8, seed=9, order="file"), 2147483647, 16, False),
+    # small primes: the iteration breaks down by chance (v^T A v == 0) long before a kernel vector is
+    # found; the reference then prints KO and writes a block that checker_modp rejects -- must be reproduced as is
+    ("cli_left_n1_p251_breakdown", lambda: synth.uniform_rows(300, 280, 5, seed=4), 251, 1, False),
+    ("cli_right_n2_p7_breakdown", lambda: synth.uniform_nnz(200, 260, 1500, seed=6, order="col"), 7, 2, True),
 ]
 
 LOOP_CASES = [
@@ -91,7 +95,10 @@ def run_loop(name, M, p, n, right, K):
 
 
 if __name__ == "__main__":
+    only = sys.argv[1:]                      # optional: regenerate just the named cases
     for c in CLI_CASES:
-        run_cli(c[0], c[1](), *c[2:])
+        if not only or c[0] in only:
+            run_cli(c[0], c[1](), *c[2:])
     for c in LOOP_CASES:
-        run_loop(c[0], c[1](), *c[2:])
+        if not only or c[0] in only:
+            run_loop(c[0], c[1](), *c[2:])
