@@ -3,6 +3,8 @@
 #include "mtx_io.h"
 #include <ctype.h>
 #include <err.h>
+#include <pthread.h>
+#include <unistd.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -85,6 +87,104 @@ static int ieq(const char *a, const char *b)
         return *a == *b;
 }
 
+/* ---- parallel triplet parser -------------------------------------------------------------
+ * The data section is a stream of white-space separated integers; entry k is integers 3k..3k+2
+ * (exactly what nnz calls of fscanf("%d %d %d\n") consume, sequential/lanczos_modp.c:236-243).
+ * The buffer is cut at white space into one segment per thread; pass 1 counts the integers that
+ * start in each segment, a prefix sum gives every segment its first global integer index, pass 2
+ * parses and stores each integer at (entry, field) = (index / 3, index % 3). */
+struct parse_seg {
+        const char *b, *e;
+        long long ntok, first;          /* integers starting in [b,e); global index of the first one */
+        long long bad;                  /* global index of the first malformed integer, or -1 */
+        long long nz;
+        uint64_t prime;
+        int *Mi, *Mj;
+        uint32_t *Mx;
+};
+
+static inline int is_space(char c) { return c == ' ' || c == '\n' || c == '\t' || c == '\r'; }
+
+static void *seg_count(void *arg)
+{
+        struct parse_seg *s = arg;
+        long long n = 0;
+        int in = 0;
+        for (const char *p = s->b; p < s->e; p++) {
+                int sp = is_space(*p);
+                n += (!sp && !in);
+                in = !sp;
+        }
+        s->ntok = n;
+        return NULL;
+}
+
+static void *seg_parse(void *arg)
+{
+        struct parse_seg *s = arg;
+        const char *p = s->b;
+        long long g = s->first, limit = 3 * s->nz;
+        s->bad = -1;
+        while (g < limit) {
+                while (p < s->e && is_space(*p)) p++;
+                if (p >= s->e) break;
+                int neg = 0;
+                if (*p == '-' || *p == '+') { neg = (*p == '-'); p++; }
+                if (p >= s->e || *p < '0' || *p > '9') { s->bad = g; return NULL; }
+                long long v = 0;
+                while (p < s->e && *p >= '0' && *p <= '9') v = v * 10 + (*p++ - '0');
+                if (p < s->e && !is_space(*p)) { s->bad = g; return NULL; }
+                if (neg) v = -v;
+                long long k = g / 3;
+                switch (g % 3) {
+                case 0: s->Mi[k] = (int)(v - 1); break;            /* MatrixMarket is 1-based */
+                case 1: s->Mj[k] = (int)(v - 1); break;
+                /* the reference reads "%d" into a u32 and then reduces: -k becomes 2^32-k (F9) */
+                default: s->Mx[k] = (uint32_t)((uint64_t)(uint32_t)(int)v % s->prime); break;
+                }
+                g++;
+        }
+        return NULL;
+}
+
+static void parse_entries(const char *b, const char *e, long long nz, uint64_t prime, int *Mi, int *Mj, uint32_t *Mx)
+{
+        enum { MAXT = 64 };
+        long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
+        const char *env = getenv("BLK_PARSE_THREADS");
+        long T = env ? atol(env) : ncpu;
+        size_t bytes = (size_t)(e - b);
+        if (T > MAXT) T = MAXT;
+        if ((size_t)T > bytes / (1u << 20) + 1) T = (long)(bytes / (1u << 20) + 1);      /* >= 1 MiB per thread */
+        if (T < 1) T = 1;
+        struct parse_seg seg[MAXT];
+        pthread_t th[MAXT];
+        const char *cut = b;
+        for (long t = 0; t < T; t++) {
+                const char *next = t == T - 1 ? e : b + bytes * (size_t)(t + 1) / (size_t)T;
+                if (next < cut) next = cut;
+                while (next < e && !is_space(*next)) next++;            /* never cut inside an integer */
+                seg[t] = (struct parse_seg){cut, next, 0, 0, -1, nz, prime, Mi, Mj, Mx};
+                cut = next;
+        }
+        for (long t = 0; t < T; t++)
+                if (T == 1 || pthread_create(&th[t], NULL, seg_count, &seg[t]) != 0) { seg_count(&seg[t]); th[t] = 0; }
+        for (long t = 0; t < T; t++)
+                if (th[t]) pthread_join(th[t], NULL);
+        long long total = 0;
+        for (long t = 0; t < T; t++) { seg[t].first = total; total += seg[t].ntok; }
+        for (long t = 0; t < T; t++)
+                if (T == 1 || pthread_create(&th[t], NULL, seg_parse, &seg[t]) != 0) { seg_parse(&seg[t]); th[t] = 0; }
+        for (long t = 0; t < T; t++)
+                if (th[t]) pthread_join(th[t], NULL);
+        long long bad = -1;
+        for (long t = 0; t < T; t++)
+                if (seg[t].bad >= 0 && (bad < 0 || seg[t].bad < bad)) bad = seg[t].bad;
+        if (bad < 0 && total < 3 * nz) bad = total;                      /* file ends early */
+        if (bad >= 0 && bad < 3 * nz)
+                errx(1, "parse error entry %lld\n", bad / 3);
+}
+
 void mtx_load(struct coo_matrix *M, const char *filename, uint64_t prime)
 {
         printf("Loading matrix from %s\n", filename);
@@ -135,16 +235,7 @@ void mtx_load(struct coo_matrix *M, const char *filename, uint64_t prime)
         if (!Mi || !Mj || !Mx)
                 err(1, "Cannot allocate sparse matrix");
 
-        const char *p = buf + pos, *end = buf + len;
-        for (long long u = 0; u < nz; u++) {
-                long long a, b, c;
-                if (!scan_int(&p, end, &a) || !scan_int(&p, end, &b) || !scan_int(&p, end, &c))
-                        errx(1, "parse error entry %lld\n", u);
-                Mi[u] = (int)(a - 1);            /* MatrixMarket is 1-based */
-                Mj[u] = (int)(b - 1);
-                /* the reference reads "%d" into a u32 and then reduces: -k becomes 2^32-k (F9) */
-                Mx[u] = (uint32_t)((uint64_t)(uint32_t)(int)c % prime);
-        }
+        parse_entries(buf + pos, buf + len, nz, prime, Mi, Mj, Mx);
         double dt = now() - t0;
         printf("  - Read %s: %.1f MB in %.2fs (%.1f MB/s)\n", filename, len / 1048576., dt,
                len / 1048576. / (dt > 0 ? dt : 1e-9));

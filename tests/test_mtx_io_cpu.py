@@ -134,3 +134,53 @@ def test_kernel_block_and_checkpoint_vectors_format(harness, tmp_path):
     assert subprocess.run([harness, "vec", raw, str(nrows * n), vec], capture_output=True).returncode == 0
     assert open(vec).read() == "".join(f"{t}\n" for t in v)
     assert not os.path.exists(vec + ".tmp")                      # written through rename()
+
+
+def test_parallel_parser_large_file(harness, tmp_path):
+    """The triplet section is parsed by several threads (whole-file read, segments cut at white
+    space, integer index -> (entry, field)); result identical to one thread and to numpy for any
+    thread count, odd white space included; the first malformed integer is reported by entry."""
+    rng = np.random.default_rng(5)
+    nnz, nrows, ncols, p = 1_200_000, 70_000, 65_000, 2147483647
+    i = rng.integers(1, nrows + 1, nnz); j = rng.integers(1, ncols + 1, nnz)
+    x = rng.integers(-50, 2 ** 31 - 1, nnz)
+    mtx = str(tmp_path / "big.mtx")
+    with open(mtx, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate integer general\n% c\n")
+        f.write(f"{nrows} {ncols} {nnz}\n")
+        rows = [f"{a} {b} {c}" for a, b, c in zip(i[:1000], j[:1000], x[:1000])]
+        # odd but legal layouts for fscanf("%d %d %d\n"): tabs, CRLF, an entry split over two lines
+        rows[3] = rows[3].replace(" ", "\t")
+        rows[5] = rows[5].replace(" ", "   ") + "\r"
+        rows[7] = rows[7].replace(" ", "\n", 1)
+        f.write("\n".join(rows) + "\n")
+        np.savetxt(f, np.stack([i[1000:], j[1000:], x[1000:]], axis=1), fmt="%d")
+    want_x = ((x + (1 << 32)) % (1 << 32)) % p
+    results = []
+    for threads in ("1", "3", "16"):
+        env = dict(os.environ, BLK_PARSE_THREADS=threads)
+        out = str(tmp_path / f"m{threads}.bin")
+        r = subprocess.run([harness, "load", mtx, str(p), out], capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stderr
+        raw = np.fromfile(out, dtype=np.uint32)
+        body = raw[4:]
+        assert np.array_equal(body[:nnz].view(np.int32), i - 1) and np.array_equal(body[nnz:2 * nnz].view(np.int32), j - 1)
+        assert np.array_equal(body[2 * nnz:], want_x.astype(np.uint32))
+        results.append(raw)
+    assert all(np.array_equal(results[0], r) for r in results[1:])
+    # malformed integer deep inside the file, and a truncated file
+    txt = open(mtx).read().split("\n")
+    bad_line = 3 + 800_000
+    txt[bad_line] = txt[bad_line].split(" ")[0] + " 12x4 7"
+    bad = str(tmp_path / "bad.mtx")
+    open(bad, "w").write("\n".join(txt))
+    for threads in ("1", "16"):
+        r = subprocess.run([harness, "load", bad, str(p), str(tmp_path / "o.bin")], capture_output=True, text=True,
+                           env=dict(os.environ, BLK_PARSE_THREADS=threads))
+        # (entry 7 occupies two lines, so file line 3 + 800000 holds entry 799999)
+        assert r.returncode == 1 and "parse error entry 799999" in r.stderr, r.stderr[-200:]
+    short = str(tmp_path / "short.mtx")
+    open(short, "w").write("\n".join(open(mtx).read().split("\n")[:3 + 500_000]) + "\n")
+    r = subprocess.run([harness, "load", short, str(p), str(tmp_path / "o.bin")], capture_output=True, text=True,
+                       env=dict(os.environ, BLK_PARSE_THREADS="8"))
+    assert r.returncode == 1 and "parse error entry" in r.stderr
