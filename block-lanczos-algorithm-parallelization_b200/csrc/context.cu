@@ -735,7 +735,6 @@ int blk_create(blk_ctx **out, const blk_params *prm)
         else { CUX(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
 
         dense_prepare(c->geo, c->m);
-        if (const char *e = getenv("BLK_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
 
         // ---- COO on the device
         const int64_t nnz = prm->nnz;
