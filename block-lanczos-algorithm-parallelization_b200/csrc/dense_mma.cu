@@ -15,9 +15,10 @@
 //       transposes with PRMT); the four warps of a block take one limb b of Y each.
 //
 // mma.sync.m16n8k32.u8.u8.s32 (SASS IMMA.16832.U8.U8) sustains 573 T int8 MAC/s on B200
-// (tools/imma_bench.cu), which puts both phases back under their HBM time, so the legacy
-// warp-level MMA is sufficient here: tcgen05/TMEM would only raise a ceiling that is no longer
-// the bound (K is the long axis for dots, M for ortho; N = 4 n_pad <= 128 either way).
+// (tools/imma_bench.cu), so the MMA rate is not the bound here; the operand preparation on the
+// SM's instruction stream is (3x / 2x the HBM time on config 4).  n_pad = 16 therefore runs on
+// the TMA-fed tcgen05 kernels of dense_umma.cu by default; these kernels serve n_pad = 8 and 32
+// and BLK_DENSE=mma.
 #include <cstdlib>
 #include "blk_internal.cuh"
 #include "small_body.cuh"

@@ -33,6 +33,7 @@
 // hang.
 #include <cuda.h>
 #include <cstdlib>
+#include <cstring>
 #include "blk_internal.cuh"
 #include "small_body.cuh"
 
@@ -521,12 +522,14 @@ constexpr size_t ORTHO_SMEM = (size_t)OSTAGES * OSTAGE_BYTES + 3 * OB_BYTES + 10
 
 int umma_mode()
 {
-        // BLK_DENSE=umma: M = 128 (one instruction for both products); BLK_DENSE=umma64: two M = 64 instructions
+        // default: M = 128 (one instruction for both products).  BLK_DENSE=umma64: two M = 64 instructions;
+        // BLK_DENSE=mma: the IMMA kernels of dense_mma.cu; BLK_DENSE=cuda: the CUDA-core kernels of dense.cu
         static int mode = -1;
         if (mode < 0) {
                 const char *e = getenv("BLK_DENSE");
-                mode = 0;
-                if (e && e[0] == 'u') mode = (e[4] == '6') ? 1 : 2;
+                mode = 2;
+                if (e && (e[0] == 'm' || e[0] == 'c')) mode = 0;
+                else if (e && e[0] == 'u' && strlen(e) > 4 && e[4] == '6') mode = 1;
         }
         return mode;
 }
