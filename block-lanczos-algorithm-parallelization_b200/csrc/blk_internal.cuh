@@ -136,7 +136,7 @@ void dense_umma_prepare(int np);
 int launch_dots_umma(int np, const ModP &m, int64_t rows, const u32 *v, const u32 *Av, u64 *sums,
                      const DevSmall *state, const SmallFuse &fuse, cudaStream_t st, int wide = -1);
 int launch_ortho_umma(int np, const ModP &m, int64_t rows, u32 *v, const u32 *Av, u32 *p, u32 *v_out, u32 *p_out,
-                      const u32 *mats, const DevSmall *state, int force, cudaStream_t st);
+                      const u32 *mats, const DevSmall *state, int force, cudaStream_t st, int variant = -1);
 // per-device one-time kernel attributes (call with the device current, outside stream capture)
 void dense_prepare(const Geometry &geo, const ModP &m);
 // n <-> n_pad repacking of row-major blocks (rows x n  <->  rows x np)

@@ -25,7 +25,7 @@
 // 128-row TMA tile of v (or p) is the K-major A operand as it stands (K = the 64 bytes of a row);
 // the B operands, limb b of (2^(8a) X[i][j] mod p) at [K = 4i + a][N = 4j + b] for X in
 // {c, vtAvd, winv}, are three 4 KB tiles every CTA derives from `mats` when it starts.  Six
-// instructions per 128 rows leave D_v = v c + p vtAvd and D_p = v winv in TMEM; eight epilogue
+// instructions per 128 rows leave D_v = v c + p vtAvd and D_p = v winv in TMEM; sixteen epilogue
 // warps recombine the limbs, add the base term, overwrite the v and p tiles in shared memory and
 // a store warp sends them back with TMA.
 //
@@ -278,10 +278,7 @@ k_dots_umma(const __grid_constant__ CUtensorMap map_v, const __grid_constant__ C
 constexpr int OT_ROWS = 128;                          // rows per tile = M of one instruction
 constexpr int OT_BYTES = OT_ROWS * ROW_BYTES;         // 8 KB per operand
 constexpr int OSTAGE_BYTES = 3 * OT_BYTES;            // v, Av, p
-constexpr int OSTAGES = 5;
 constexpr int OB_BYTES = 64 * ROW_BYTES;              // one B operand: K = 64 rows of 64 bytes
-constexpr int OEPI_WARPS = 8;
-constexpr int OTHREADS = (OEPI_WARPS + 3) * 32;       // + producer, MMA issuer, store warp
 
 // K-major, SWIZZLE_64B: rows (M) 64 bytes apart, 8-row groups 512 bytes apart (SBO); `addr` may
 // point 32 bytes into the row for the second K step
@@ -302,11 +299,17 @@ __host__ __device__ constexpr uint32_t i8_idesc_kmaj_a(int M, int N)
         return (2u << 4) | (0u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ void tmem_ld16(uint32_t (&r)[16], uint32_t taddr)
+// this thread's TMEM lane, CW (32 or 64) consecutive columns
+template <int CW> __device__ __forceinline__ void tmem_ld_cols(uint32_t (&r)[CW], uint32_t taddr);
+template <> __device__ __forceinline__ void tmem_ld_cols<64>(uint32_t (&r)[64], uint32_t taddr) { tmem_ld64(r, taddr); }
+template <> __device__ __forceinline__ void tmem_ld_cols<32>(uint32_t (&r)[32], uint32_t taddr)
 {
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                     "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
                      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                       "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                       "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                      : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -329,31 +332,43 @@ __device__ __forceinline__ void tma_store_rows(const CUtensorMap *map, uint32_t 
                      :: "l"(map), "r"(0), "r"(row0), "r"(src) : "memory");
 }
 
-__global__ void __launch_bounds__(OTHREADS, 1)
+// sum_b 2^(8b) r_b mod p for limb sums r_b <= 128 * 255^2 < 2^23 (K = 128 bytes per output):
+// both halves fit 32 bits, so the recombination is two shifts-and-adds and one wide multiply-add
+__device__ __forceinline__ u32 recombine23(u32 r0, u32 r1, u32 r2, u32 r3, const ModP &m)
+{
+        const u32 lo = r0 + (r1 << 8), hi = r2 + (r3 << 8);
+        return mp_reduce((u64)hi * 65536ull + lo, m);
+}
+
+// CW = accumulator columns per epilogue warp (64: 8 warps, 32: 16 warps); S = tiles in flight
+template <int CW, int S>
+__global__ void __launch_bounds__((2 * 4 * 64 / CW + 3) * 32, 1)
 k_ortho_umma(const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_av,
              const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_vout,
              const __grid_constant__ CUtensorMap map_pout, int64_t ntile, const u32 *__restrict__ mats, ModP m,
              const DevSmall *__restrict__ state, int force)
 {
         constexpr int NP = 16;
+        constexpr int EPI = 2 * 4 * 64 / CW;                        // epilogue warps
+        constexpr int NTHR = (EPI + 3) * 32;                        // + producer, MMA issuer, store warp
         extern __shared__ uint8_t dyn_raw[];
-        __shared__ __align__(8) uint64_t bars[3 * OSTAGES + 4];
+        __shared__ __align__(8) uint64_t bars[3 * S + 4];
         __shared__ uint32_t tmem_slot;
         if (!force && !state->do_ortho) return;
 
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         const uint32_t bmat0 = (smem_u32(dyn_raw) + 1023u) & ~1023u;       // Bc, Bd, Bw
         const uint32_t stage0 = bmat0 + 3 * OB_BYTES;
-        const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[OSTAGES]);
-        const uint32_t bar_out = smem_u32(&bars[2 * OSTAGES]);
-        const uint32_t bar_acc_full = smem_u32(&bars[3 * OSTAGES]), bar_acc_empty = smem_u32(&bars[3 * OSTAGES + 2]);
+        const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[S]);
+        const uint32_t bar_out = smem_u32(&bars[2 * S]);
+        const uint32_t bar_acc_full = smem_u32(&bars[3 * S]), bar_acc_empty = smem_u32(&bars[3 * S + 2]);
 
         const int64_t t_lo = ntile * blockIdx.x / gridDim.x, t_hi = ntile * (blockIdx.x + 1) / gridDim.x;
         const int my = (int)(t_hi - t_lo);
 
         // B operands: row k = 4i + a holds the 16 words (2^(8a) X[i][j] mod p), j = 0..15, with the
         // 16-byte chunks of a row XOR-swizzled like TMA SWIZZLE_64B does (chunk ^= (k >> 1) & 3)
-        for (int e = threadIdx.x; e < 3 * 64 * NP; e += OTHREADS) {
+        for (int e = threadIdx.x; e < 3 * 64 * NP; e += NTHR) {
                 const int j = e & 15, k = (e >> 4) & 63, X = e >> 10;
                 const int which = X == 0 ? MAT_C : (X == 1 ? MAT_VTAVD : MAT_WINV);
                 const u32 x = mats[which * NP * NP + (k >> 2) * NP + j];
@@ -366,13 +381,13 @@ k_ortho_umma(const __grid_constant__ CUtensorMap map_v, const __grid_constant__ 
         for (int j = 0; j < NP; j++) dmask |= (mats[MAT_D * NP * NP + j] != 0 ? 1u : 0u) << j;
 
         if (threadIdx.x == 0) {
-                for (int s = 0; s < OSTAGES; s++) {
-                        mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); mbar_init(bar_out + 8 * s, OEPI_WARPS * 32);
+                for (int s = 0; s < S; s++) {
+                        mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); mbar_init(bar_out + 8 * s, EPI * 32);
                 }
-                for (int b = 0; b < 2; b++) { mbar_init(bar_acc_full + 8 * b, 1); mbar_init(bar_acc_empty + 8 * b, OEPI_WARPS * 32); }
+                for (int b = 0; b < 2; b++) { mbar_init(bar_acc_full + 8 * b, 1); mbar_init(bar_acc_empty + 8 * b, EPI * 32); }
                 asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        if (warp == OEPI_WARPS) {
+        if (warp == EPI) {
                 asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" :: "r"(smem_u32(&tmem_slot)));
                 asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
         }
@@ -381,11 +396,11 @@ k_ortho_umma(const __grid_constant__ CUtensorMap map_v, const __grid_constant__ 
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem = tmem_slot;
 
-        if (warp == OEPI_WARPS) {
+        if (warp == EPI) {
                 if (lane == 0) {                                   // ---- TMA producer
                         for (int t = 0; t < my; t++) {
-                                const int s = t % OSTAGES;
-                                mbar_wait(bar_empty + 8 * s, ((uint32_t)(t / OSTAGES) & 1u) ^ 1u);
+                                const int s = t % S;
+                                mbar_wait(bar_empty + 8 * s, ((uint32_t)(t / S) & 1u) ^ 1u);
                                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
                                              :: "r"(bar_full + 8 * s), "r"(OSTAGE_BYTES) : "memory");
                                 const int row0 = (int)((t_lo + t) * OT_ROWS);
@@ -396,12 +411,12 @@ k_ortho_umma(const __grid_constant__ CUtensorMap map_v, const __grid_constant__ 
                         }
                 }
                 __syncwarp();
-        } else if (warp == OEPI_WARPS + 1) {
+        } else if (warp == EPI + 1) {
                 if (lane == 0) {                                   // ---- MMA issuer
                         constexpr uint32_t idesc = i8_idesc_kmaj_a(128, 64);
                         for (int t = 0; t < my; t++) {
-                                const int s = t % OSTAGES, b = t & 1;
-                                mbar_wait(bar_full + 8 * s, (uint32_t)(t / OSTAGES) & 1u);
+                                const int s = t % S, b = t & 1;
+                                mbar_wait(bar_full + 8 * s, (uint32_t)(t / S) & 1u);
                                 mbar_wait(bar_acc_empty + 8 * b, (((uint32_t)t >> 1) & 1u) ^ 1u);
                                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                                 const uint32_t sv = stage0 + s * OSTAGE_BYTES, sp = sv + 2 * OT_BYTES;
@@ -418,11 +433,11 @@ k_ortho_umma(const __grid_constant__ CUtensorMap map_v, const __grid_constant__ 
                         }
                 }
                 __syncwarp();
-        } else if (warp == OEPI_WARPS + 2) {
+        } else if (warp == EPI + 2) {
                 if (lane == 0) {                                   // ---- TMA store of finished tiles
                         for (int t = 0; t < my; t++) {
-                                const int s = t % OSTAGES;
-                                mbar_wait(bar_out + 8 * s, (uint32_t)(t / OSTAGES) & 1u);
+                                const int s = t % S;
+                                mbar_wait(bar_out + 8 * s, (uint32_t)(t / S) & 1u);
                                 const int row0 = (int)((t_lo + t) * OT_ROWS);
                                 const uint32_t sb = stage0 + s * OSTAGE_BYTES;
                                 tma_store_rows(&map_vout, sb, row0);
@@ -434,56 +449,50 @@ k_ortho_umma(const __grid_constant__ CUtensorMap map_v, const __grid_constant__ 
                         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
                 }
                 __syncwarp();
-        } else {                                                   // ---- epilogue warps 0-7
-                const int q = warp & 3, half = warp >> 2;          // TMEM lane quarter; 0: new v, 1: new p
+        } else {                                                   // ---- epilogue warps
+                // warp -> TMEM lane quarter q (hardware rule: warp % 4), output half (0: new v, 1: new p)
+                // and, for CW = 32, which 32 of the 64 accumulator columns
+                const int q = warp & 3, part = warp >> 2;
+                const int half = part / (64 / CW), col0 = (part % (64 / CW)) * CW;
                 const int row = q * 32 + lane;
                 const uint32_t rsw = ((uint32_t)row >> 1) & 3u;
                 for (int t = 0; t < my; t++) {
-                        const int s = t % OSTAGES, b = t & 1;
-                        mbar_wait(bar_full + 8 * s, (uint32_t)(t / OSTAGES) & 1u);         // the tile's bytes (TMA)
+                        const int s = t % S, b = t & 1;
+                        mbar_wait(bar_full + 8 * s, (uint32_t)(t / S) & 1u);               // the tile's bytes (TMA)
+                        const uint32_t sb = stage0 + s * OSTAGE_BYTES + row * ROW_BYTES;
+                        // base terms first: they do not depend on the products
+                        uint4 base[CW / 16], alt[CW / 16];
+#pragma unroll
+                        for (int c = 0; c < CW / 16; c++) {
+                                const uint32_t off = ((uint32_t)(col0 / 16 + c) ^ rsw) << 4;
+                                if (half == 0) { base[c] = lds128(sb + off); alt[c] = lds128(sb + OT_BYTES + off); }
+                                else { base[c] = lds128(sb + 2 * OT_BYTES + off); alt[c] = make_uint4(0, 0, 0, 0); }
+                        }
                         mbar_wait(bar_acc_full + 8 * b, ((uint32_t)t >> 1) & 1u);          // its products
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + b * 128 + half * 64;
-                        const uint32_t sb = stage0 + s * OSTAGE_BYTES + row * ROW_BYTES;
-#pragma unroll
-                        for (int c = 0; c < 4; c++) {
-                                uint32_t r[16];
-                                tmem_ld16(r, taddr + 16 * c);
-                                const uint32_t off = ((uint32_t)c ^ rsw) << 4;
-                                u32 o[4];
-#pragma unroll
-                                for (int k = 0; k < 4; k++) {
-                                        u64 x = (u64)r[4 * k] + ((u64)r[4 * k + 1] << 8) + ((u64)r[4 * k + 2] << 16) + ((u64)r[4 * k + 3] << 24);
-                                        o[k] = mp_reduce(x, m);
-                                }
-                                const u32 dm = dmask >> (4 * c);
-                                if (half == 0) {
-                                        // new v = v c + p vtAvd + (d ? Av : v)      (:484-489)
-                                        const uint4 vq = lds128(sb + off), aq = lds128(sb + OT_BYTES + off);
-                                        o[0] = mp_add(o[0], (dm & 1u) ? aq.x : vq.x, m);
-                                        o[1] = mp_add(o[1], (dm & 2u) ? aq.y : vq.y, m);
-                                        o[2] = mp_add(o[2], (dm & 4u) ? aq.z : vq.z, m);
-                                        o[3] = mp_add(o[3], (dm & 8u) ? aq.w : vq.w, m);
-                                        sts128(sb + off, make_uint4(o[0], o[1], o[2], o[3]));
-                                } else {
-                                        // new p = v winv + (d ? 0 : p)
-                                        const uint4 pq = lds128(sb + 2 * OT_BYTES + off);
-                                        o[0] = mp_add(o[0], (dm & 1u) ? 0u : pq.x, m);
-                                        o[1] = mp_add(o[1], (dm & 2u) ? 0u : pq.y, m);
-                                        o[2] = mp_add(o[2], (dm & 4u) ? 0u : pq.z, m);
-                                        o[3] = mp_add(o[3], (dm & 8u) ? 0u : pq.w, m);
-                                        sts128(sb + 2 * OT_BYTES + off, make_uint4(o[0], o[1], o[2], o[3]));
-                                }
-                        }
+                        uint32_t r[CW];
+                        tmem_ld_cols<CW>(r, tmem + ((uint32_t)(q * 32) << 16) + b * 128 + half * 64 + col0);
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                         mbar_arrive(bar_acc_empty + 8 * b);
+#pragma unroll
+                        for (int c = 0; c < CW / 16; c++) {
+                                // new v = v c + p vtAvd + (d ? Av : v);  new p = v winv + (d ? 0 : p)      (:484-489)
+                                const u32 dm = dmask >> (col0 / 4 + 4 * c);
+                                uint4 o;
+                                o.x = mp_add(recombine23(r[16 * c + 0], r[16 * c + 1], r[16 * c + 2], r[16 * c + 3], m), (dm & 1u) ? alt[c].x : base[c].x, m);
+                                o.y = mp_add(recombine23(r[16 * c + 4], r[16 * c + 5], r[16 * c + 6], r[16 * c + 7], m), (dm & 2u) ? alt[c].y : base[c].y, m);
+                                o.z = mp_add(recombine23(r[16 * c + 8], r[16 * c + 9], r[16 * c + 10], r[16 * c + 11], m), (dm & 4u) ? alt[c].z : base[c].z, m);
+                                o.w = mp_add(recombine23(r[16 * c + 12], r[16 * c + 13], r[16 * c + 14], r[16 * c + 15], m), (dm & 8u) ? alt[c].w : base[c].w, m);
+                                const uint32_t off = ((uint32_t)(col0 / 16 + c) ^ rsw) << 4;
+                                sts128(sb + (half ? 2 * OT_BYTES : 0) + off, o);
+                        }
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // tile writes -> TMA store
                         mbar_arrive(bar_out + 8 * s);
                 }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        if (warp == OEPI_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" :: "r"(tmem));
+        if (warp == EPI) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" :: "r"(tmem));
 }
 
 typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -518,7 +527,8 @@ bool row_map(CUtensorMap *map, const void *base, int64_t rows, int box_rows = TI
 }
 
 constexpr size_t DOTS_SMEM = (size_t)STAGES * 2 * TILE_BYTES + 1024;
-constexpr size_t ORTHO_SMEM = (size_t)OSTAGES * OSTAGE_BYTES + 3 * OB_BYTES + 1024;
+constexpr int ORTHO_DEFAULT_VARIANT = 3;          // 16 epilogue warps, 7 tiles in flight: 2.63 ms on config 4 (variant 0: 3.5 ms)
+constexpr size_t ortho_smem(int stages) { return (size_t)stages * OSTAGE_BYTES + 3 * OB_BYTES + 1024; }
 
 int umma_mode()
 {
@@ -546,7 +556,10 @@ void dense_umma_prepare(int np)
         if (np != 16) return;
         cudaFuncSetAttribute(k_dots_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DOTS_SMEM);
         cudaFuncSetAttribute(k_dots_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DOTS_SMEM);
-        cudaFuncSetAttribute(k_ortho_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ORTHO_SMEM);
+        cudaFuncSetAttribute(k_ortho_umma<64, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ortho_smem(5));
+        cudaFuncSetAttribute(k_ortho_umma<64, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ortho_smem(7));
+        cudaFuncSetAttribute(k_ortho_umma<32, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ortho_smem(5));
+        cudaFuncSetAttribute(k_ortho_umma<32, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ortho_smem(7));
 }
 
 // wide < 0: follow BLK_DENSE
@@ -566,8 +579,9 @@ int launch_dots_umma(int np, const ModP &m, int64_t rows, const u32 *v, const u3
         return 1;
 }
 
+// variant: 0..3 = (8 epilogue warps, 5 tiles in flight), (8, 7), (16, 5), (16, 7); < 0: the default
 int launch_ortho_umma(int np, const ModP &m, int64_t rows, u32 *v, const u32 *Av, u32 *p, u32 *v_out, u32 *p_out,
-                      const u32 *mats, const DevSmall *state, int force, cudaStream_t st)
+                      const u32 *mats, const DevSmall *state, int force, cudaStream_t st, int variant)
 {
         if (np != 16) return -1;
         CUtensorMap mv, ma, mp, mvo, mpo;
@@ -576,6 +590,12 @@ int launch_ortho_umma(int np, const ModP &m, int64_t rows, u32 *v, const u32 *Av
                 return -1;
         const int64_t ntile = (rows + OT_ROWS - 1) / OT_ROWS;
         const unsigned grid = (unsigned)(ntile < 148 ? ntile : 148);
-        k_ortho_umma<<<grid, OTHREADS, ORTHO_SMEM, st>>>(mv, ma, mp, mvo, mpo, ntile, mats, m, state, force);
+        if (variant < 0) variant = ORTHO_DEFAULT_VARIANT;
+        switch (variant) {
+        case 0: k_ortho_umma<64, 5><<<grid, 11 * 32, ortho_smem(5), st>>>(mv, ma, mp, mvo, mpo, ntile, mats, m, state, force); break;
+        case 1: k_ortho_umma<64, 7><<<grid, 11 * 32, ortho_smem(7), st>>>(mv, ma, mp, mvo, mpo, ntile, mats, m, state, force); break;
+        case 2: k_ortho_umma<32, 5><<<grid, 19 * 32, ortho_smem(5), st>>>(mv, ma, mp, mvo, mpo, ntile, mats, m, state, force); break;
+        default: k_ortho_umma<32, 7><<<grid, 19 * 32, ortho_smem(7), st>>>(mv, ma, mp, mvo, mpo, ntile, mats, m, state, force); break;
+        }
         return 1;
 }

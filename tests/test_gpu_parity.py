@@ -117,6 +117,28 @@ def test_dense_functions_match_oracle(lib, oracle, n, p):
                 assert np.array_equal(go[0], wo[0]) and np.array_equal(go[1], wo[1]), (N, trial, "ortho")
 
 
+@pytest.mark.parametrize("n,p", [(16, P_MERSENNE), (16, P_FERMAT), (12, P_CAP)])
+def test_dense_functions_many_tiles(lib, oracle, n, p):
+    """Row counts at which every SM works through several tiles (stage reuse, partial last tile) of the
+    tensor-core kernels: dots and orthogonalize against the oracle, bit for bit."""
+    rng = np.random.default_rng(1000 + n)
+    M = lib.synth.uniform_rows(40, 30, 3).reduced(p)
+    with lib.BlockLanczos(M, n=n, prime=p) as ctx:
+        for N in (148 * 256 * 5 + 11,):
+            v, Av, pb = (rng.integers(0, p, size=N * n).astype(np.uint32) for _ in range(3))
+            v[::7] = p - 1; Av[::5] = p - 1; pb[::3] = p - 1
+            got, want = ctx.block_dot_products(N, Av, v), oracle.block_dot_products(N, Av, v, n, p)
+            assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), (N, "dots")
+            U = rng.integers(0, p, size=(n, n)).astype(np.uint64)
+            U = ((U + U.T) % p).astype(np.uint32)
+            U[:, n // 2] = 0; U[n // 2, :] = 0          # one zero pivot: d mixes 0 and 1
+            w = oracle.semi_inverse(U.ravel(), n, p)
+            vt, vtt = (rng.integers(0, p, size=n * n).astype(np.uint32) for _ in range(2))
+            go = ctx.orthogonalize(v, pb, w[2], vt, vtt, w[1], N, Av)
+            wo = oracle.orthogonalize(v, pb, w[2], vt, vtt, w[1], N, Av, n, p)
+            assert np.array_equal(go[0], wo[0]) and np.array_equal(go[1], wo[1]), (N, "ortho")
+
+
 @pytest.mark.parametrize("name", golden_cases("loop_"))
 def test_loop_state_matches_reference_golden(lib, name):
     z, M = load_golden(name)

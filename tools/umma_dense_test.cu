@@ -96,7 +96,7 @@ static int test_dots(int wide, const std::vector<int64_t> &sizes)
                         printf("  dots %s rows %lld p %u: %s", wide ? "M=128" : "2xM=64", (long long)rows, m.p, wrong ? "MISMATCH" : "identical");
                         if (wrong) {
                                 printf(" (%d of 512; first: matrix %d i %d j %d want %llu got %llu)", wrong, first >> 8, (first >> 4) & 15, first & 15,
-                                       h[first] % m.p, h[512 + first] % m.p);
+                                       (unsigned long long)(h[first] % m.p), (unsigned long long)(h[512 + first] % m.p));
                                 int by_m[2] = {0, 0};
                                 for (int i = 0; i < 512; i++) by_m[i >> 8] += h[i] % m.p != h[512 + i] % m.p;
                                 printf(" vtAv %d vtAAv %d", by_m[0], by_m[1]);
@@ -189,24 +189,29 @@ static int test_ortho(const std::vector<int64_t> &sizes)
                         for (int w = 0; w < 2; w++) { CK(cudaMemset(vo[w], 0xcd, rows * 64)); CK(cudaMemset(po[w], 0xcd, rows * 64)); }
                         launch_ortho_mma(16, m, rows, v, Av, p, vo[0], po[0], mats, nullptr, 1, 0);
                         CK(cudaDeviceSynchronize());
-                        if (launch_ortho_umma(16, m, rows, v, Av, p, vo[1], po[1], mats, nullptr, 1, 0) != 1) { printf("FAIL launch_ortho_umma refused\n"); return 1; }
-                        cudaError_t e = cudaDeviceSynchronize();
-                        if (e != cudaSuccess) { printf("FAIL ortho kernel (rows %lld): %s\n", (long long)rows, cudaGetErrorString(e)); return 1; }
                         printf(" ortho rows %lld p %u\n", (long long)rows, m.p);
-                        bad += !diff("new v", vo[0], vo[1], rows);
-                        bad += !diff("new p", po[0], po[1], rows);
+                        for (int var = 0; var < 4; var++) {
+                                CK(cudaMemset(vo[1], 0xcd, rows * 64)); CK(cudaMemset(po[1], 0xcd, rows * 64));
+                                if (launch_ortho_umma(16, m, rows, v, Av, p, vo[1], po[1], mats, nullptr, 1, 0, var) != 1) { printf("FAIL launch_ortho_umma refused\n"); return 1; }
+                                cudaError_t e = cudaDeviceSynchronize();
+                                if (e != cudaSuccess) { printf("FAIL ortho kernel variant %d (rows %lld): %s\n", var, (long long)rows, cudaGetErrorString(e)); return 1; }
+                                char what[64];
+                                snprintf(what, sizeof what, "variant %d new v", var); bad += !diff(what, vo[0], vo[1], rows);
+                                snprintf(what, sizeof what, "variant %d new p", var); bad += !diff(what, po[0], po[1], rows);
+                        }
                         if (pi == 0 && rows >= 1000000) {
-                                for (int which = 0; which < 2; which++) {
+                                for (int which = -1; which < 4; which++) {
                                         float best = 1e9f;
                                         for (int rep = 0; rep < 5; rep++) {
                                                 CK(cudaEventRecord(e0));
-                                                if (which) launch_ortho_umma(16, m, rows, v, Av, p, vo[1], po[1], mats, nullptr, 1, 0);
+                                                if (which >= 0) launch_ortho_umma(16, m, rows, v, Av, p, vo[1], po[1], mats, nullptr, 1, 0, which);
                                                 else launch_ortho_mma(16, m, rows, v, Av, p, vo[0], po[0], mats, nullptr, 1, 0);
                                                 CK(cudaEventRecord(e1));
                                                 float ms = time_ms(e0, e1);
                                                 if (rep && ms < best) best = ms;
                                         }
-                                        printf("    %-8s %.3f ms  (%.0f GB/s of 3 reads + 2 writes)\n", which ? "tcgen05" : "IMMA", best, rows * 320.0 / best * 1e-6);
+                                        const char *names[5] = {"IMMA", "tcgen05 8 epilogue warps, 5 tiles", "tcgen05 8 warps, 7 tiles", "tcgen05 16 warps, 5 tiles", "tcgen05 16 warps, 7 tiles"};
+                                        printf("    %-36s %.3f ms  (%.0f GB/s of 3 reads + 2 writes)\n", names[which + 1], best, rows * 320.0 / best * 1e-6);
                                 }
                         }
                         // in place, as the iteration calls it (v_out = v, p_out = p)
