@@ -27,7 +27,7 @@ PHASES = ("spmv1", "spmv2", "dots", "small", "ortho", "exchange")
 # every symbol include/blk_lanczos.h declares
 ABI_SYMBOLS = (
     "blk_abi_version", "blk_last_error", "blk_device_count", "blk_nccl_unique_id", "blk_create",
-    "blk_destroy", "blk_plan_shards", "blk_block_pad", "blk_set_state", "blk_iterate", "blk_get_state", "blk_final_check",
+    "blk_destroy", "blk_plan_shards", "blk_plan_grid", "blk_block_pad", "blk_set_state", "blk_iterate", "blk_get_state", "blk_final_check",
     "blk_check_kernel_block", "blk_get_small",
     "blk_spmv", "blk_block_dot_products", "blk_semi_inverse", "blk_orthogonalize",
     "blk_set_profiling", "blk_get_phase_times", "blk_time_spmv", "blk_kernel_launches", "blk_get_info",
@@ -78,6 +78,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.blk_create.argtypes = [C.POINTER(vp), C.POINTER(blk_params)]
     L.blk_destroy.argtypes = [vp]
     L.blk_plan_shards.argtypes = [vp, i64, i64, i32, vp]
+    L.blk_plan_grid.argtypes = [vp, vp, i64, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     L.blk_block_pad.argtypes = [i32, i32, i32, i32]
     L.blk_block_pad.restype = i64
     L.blk_set_state.argtypes = [vp, vp, vp, i32]
@@ -123,6 +124,29 @@ def plan_shards(idx, dim: int, world: int) -> np.ndarray:
     if L.blk_plan_shards(_ptr(idx), idx.size, dim, world, _ptr(off)):
         raise BlkError(L.blk_last_error().decode())
     return off
+
+
+def plan_grid(M, right: bool, world: int, grid=(0, 0)) -> dict:
+    """The P x Q block grid of blk_plan_grid (host only): dict(P, Q, n_off, m_off, n_sub[P][Q+1],
+    m_sub[Q][P+1], block_nnz[P][Q]).  grid=(0, 0) chooses the factorisation like MPI_Dims_create."""
+    L = load_library()
+    i = np.ascontiguousarray(M.i, dtype=np.int32)
+    j = np.ascontiguousarray(M.j, dtype=np.int32)
+    g = (C.c_int32 * 2)(int(grid[0]), int(grid[1]))
+    if grid[0] and grid[1]:
+        P, Q = int(grid[0]), int(grid[1])
+    else:
+        P = Q = world          # upper bounds for the output buffers
+    n_off, m_off = np.zeros(P + 1, np.int64), np.zeros(Q + 1, np.int64)
+    n_sub, m_sub = np.zeros(P * (Q + 1) + world + 1, np.int64), np.zeros(Q * (P + 1) + world + 1, np.int64)
+    bn = np.zeros(P * Q, np.int64)
+    if L.blk_plan_grid(_ptr(i), _ptr(j), i.size, M.nrows, M.ncols, int(bool(right)), world, g, _ptr(n_off), _ptr(m_off),
+                       _ptr(n_sub), _ptr(m_sub), _ptr(bn)):
+        raise BlkError(L.blk_last_error().decode())
+    P, Q = int(g[0]), int(g[1])
+    return dict(P=P, Q=Q, n_off=n_off[:P + 1].copy(), m_off=m_off[:Q + 1].copy(),
+                n_sub=n_sub[:P * (Q + 1)].reshape(P, Q + 1).copy(), m_sub=m_sub[:Q * (P + 1)].reshape(Q, P + 1).copy(),
+                block_nnz=bn[:P * Q].reshape(P, Q).copy())
 
 
 def nccl_unique_id() -> bytes:

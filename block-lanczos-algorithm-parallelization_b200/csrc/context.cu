@@ -656,6 +656,47 @@ int blk_plan_shards(const int32_t *idx, int64_t nnz, int64_t dim, int32_t world,
         return 0;
 }
 
+int blk_plan_grid(const int32_t *Mi, const int32_t *Mj, int64_t nnz, int32_t nrows, int32_t ncols, int32_t right_kernel,
+                  int32_t world, int32_t grid[2], int64_t *n_off, int64_t *m_off, int64_t *n_sub, int64_t *m_sub,
+                  int64_t *block_nnz)
+{
+        if (!grid || !n_off || !m_off || !n_sub || !m_sub || world < 1 || nrows < 0 || ncols < 0 || (nnz > 0 && (!Mi || !Mj)))
+                return fail("blk_plan_grid: bad argument");
+        int P = grid[0], Q = grid[1];
+        if (P == 0 && Q == 0) {
+                // MPI_Dims_create(world, 2): the most square factorisation, larger factor first
+                Q = 1;
+                for (int q = 1; (int64_t)q * q <= world; q++)
+                        if (world % q == 0) Q = q;
+                P = world / Q;
+        }
+        if (P < 1 || Q < 1 || (int64_t)P * Q != world) return fail("blk_plan_grid: grid does not match world");
+        const int64_t N = right_kernel ? ncols : nrows, Mc = right_kernel ? nrows : ncols;
+        const int32_t *iN = right_kernel ? Mj : Mi, *iM = right_kernel ? Mi : Mj;
+        std::vector<u32> cn((size_t)N, 0), cm((size_t)Mc, 0);
+        for (int64_t s = 0; s < nnz; s++) {
+                if (iN[s] < 0 || iN[s] >= N || iM[s] < 0 || iM[s] >= Mc) return fail("blk_plan_grid: index out of range");
+                cn[(size_t)iN[s]]++; cm[(size_t)iM[s]]++;
+        }
+        std::vector<int64_t> no = partition_rows(cn, P), mo = partition_rows(cm, Q);
+        for (int a = 0; a <= P; a++) n_off[a] = no[a];
+        for (int b = 0; b <= Q; b++) m_off[b] = mo[b];
+        // owned pieces: dense work and exchange volume go with rows, so blocks are cut into equal row counts
+        for (int a = 0; a < P; a++)
+                for (int b = 0; b <= Q; b++) n_sub[(size_t)a * (Q + 1) + b] = no[a] + (no[a + 1] - no[a]) * b / Q;
+        for (int b = 0; b < Q; b++)
+                for (int a = 0; a <= P; a++) m_sub[(size_t)b * (P + 1) + a] = mo[b] + (mo[b + 1] - mo[b]) * a / P;
+        if (block_nnz) {
+                std::vector<int> bn((size_t)N), bm((size_t)Mc);
+                for (int a = 0; a < P; a++) for (int64_t r = no[a]; r < no[a + 1]; r++) bn[(size_t)r] = a;
+                for (int b = 0; b < Q; b++) for (int64_t r = mo[b]; r < mo[b + 1]; r++) bm[(size_t)r] = b;
+                for (int e = 0; e < P * Q; e++) block_nnz[e] = 0;
+                for (int64_t s = 0; s < nnz; s++) block_nnz[(size_t)bn[(size_t)iN[s]] * Q + bm[(size_t)iM[s]]]++;
+        }
+        grid[0] = P; grid[1] = Q;
+        return 0;
+}
+
 int64_t blk_block_pad(int32_t nrows, int32_t ncols, int32_t n, int32_t right_kernel)
 {
         int64_t N = right_kernel ? ncols : nrows, Mc = right_kernel ? nrows : ncols;

@@ -85,6 +85,24 @@ int  blk_destroy(blk_ctx *ctx);
  * (mpi/lanczos_modp.c:590-620); here blocks are balanced by non-zeros + rows. */
 int  blk_plan_shards(const int32_t *idx, int64_t nnz, int64_t dim, int32_t world, int64_t *offsets);
 
+/* Host-only: the P x Q block grid of a `world`-GPU job -- the reference's 2-D decomposition
+ * (mpi/lanczos_modp.c:532-547: MPI_Dims_create + row/column communicators; :590-620: rows split over
+ * dims[0], columns over dims[1], remainder on coordinate 0), here balanced by non-zeros.
+ * N = length of the Lanczos vectors (rows of M for --left, columns for --right), Mc = the other dimension.
+ *   grid[2]  in: {P, Q} with P*Q == world, or {0, 0} to choose like MPI_Dims_create (P >= Q, most square);
+ *            out: the grid used.  Rank of grid coordinate (a, b) = a*Q + b.
+ *   n_off[P+1], m_off[Q+1]   block boundaries along N and along Mc; rank (a,b) stores the non-zeros with
+ *            N-index in [n_off[a], n_off[a+1]) and Mc-index in [m_off[b], m_off[b+1]).
+ *   n_sub[P*(Q+1)]  row block a cut into Q pieces: rank (a,b) owns rows [n_sub[a*(Q+1)+b], n_sub[a*(Q+1)+b+1])
+ *            of v, Av and p (all-gathered / reduce-scattered inside grid row a).
+ *   m_sub[Q*(P+1)]  column block b cut into P pieces: rank (a,b) owns rows [m_sub[b*(P+1)+a], ..+1]) of tmp.
+ *   block_nnz[P*Q]  (nullable) non-zeros per block.
+ * Exchange volume per rank and iteration: 2*[(N/P)(Q-1)/Q + (Mc/Q)(P-1)/P] rows, against 2*(W-1)/W*(N+Mc)/2
+ * for the 1-D row sharding of blk_create. */
+int  blk_plan_grid(const int32_t *Mi, const int32_t *Mj, int64_t nnz, int32_t nrows, int32_t ncols,
+                   int32_t right_kernel, int32_t world, int32_t grid[2], int64_t *n_off, int64_t *m_off,
+                   int64_t *n_sub, int64_t *m_sub, int64_t *block_nnz);
+
 /* block_size_pad of block_lanczos (:594-597) in u32 elements: the length of the
  * reference's v/tmp/Av/p blocks and of every block in blk_get_state. */
 int64_t blk_block_pad(int32_t nrows, int32_t ncols, int32_t n, int32_t right_kernel);
