@@ -142,3 +142,26 @@ def test_cli_wide_matrix_tmp_tail(driver, lib, tmp_path):
     run([ref_exe, *args], cwd=str(theirs), env=dict(os.environ, OMP_NUM_THREADS="1"))
     for f in ("v.txt", "tmp.txt", "Av.txt", "p.txt"):
         assert sha(ours / f) == sha(theirs / f), f
+
+
+@pytest.mark.parametrize("n", [16, 13])
+def test_cli_dense_kernel_families_agree(driver, lib, tmp_path, n):
+    """n_pad = 16 has two tensor-core implementations of the dense phases: tcgen05 + TMA (default;
+    BLK_DENSE=umma64 = its two-instruction variant) and mma.sync int8 (BLK_DENSE=mma).  Whole runs must
+    end in byte-identical kernel files, accepted by the reference's checker."""
+    p = 2147483647
+    M = lib.synth.powerlaw_rows(2800, 3000, mean=9, seed=21, with_empty_rows=7)      # more columns than rows: a right kernel exists
+    mtx = str(tmp_path / "m.mtx")
+    lib.synth.write_mtx(mtx, M)
+    hashes = {}
+    for mode in ("", "umma64", "mma"):
+        out = str(tmp_path / f"k_{mode or 'default'}.mtx")
+        env = dict(os.environ)
+        env.pop("BLK_DENSE", None)
+        if mode:
+            env["BLK_DENSE"] = mode
+        r = run([driver, "--matrix", mtx, "--prime", str(p), "--n", str(n), "--right", "--output-file", out], env=env)
+        assert "OK:    v != 0" in r.stdout and "OK: vt*M == 0" in r.stdout
+        hashes[mode or "default"] = sha(out)
+    assert len(set(hashes.values())) == 1, hashes
+    assert checker(mtx, p, str(tmp_path / "k_default.mtx"), "--right")
