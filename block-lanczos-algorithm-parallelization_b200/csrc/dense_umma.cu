@@ -57,13 +57,20 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
 }
 
+// HINT: pass a suspend-time hint (ns) so that a waiting warp is parked by the hardware instead of
+// re-issuing try_wait from its instruction stream (experiment: variants 4-7 of the orthogonalize kernel)
+template <bool HINT = false>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
         const long long t0 = clock64();
         do {
                 uint32_t ok;
-                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                             : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+                if (HINT)
+                        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+                                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+                else
+                        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
                 if (ok) return;
         } while (clock64() - t0 < BLK_UMMA_TIMEOUT_CYCLES);
         __trap();          // no progress for seconds: fail the launch instead of hanging the GPU
@@ -340,8 +347,9 @@ __device__ __forceinline__ u32 recombine23(u32 r0, u32 r1, u32 r2, u32 r3, const
         return mp_reduce((u64)hi * 65536ull + lo, m);
 }
 
-// CW = accumulator columns per epilogue warp (64: 8 warps, 32: 16 warps); S = tiles in flight
-template <int CW, int S>
+// CW = accumulator columns per epilogue warp (64: 8 warps, 32: 16 warps); S = tiles in flight;
+// SH = epilogue warps wait with a suspend-time hint
+template <int CW, int S, bool SH = false>
 __global__ void __launch_bounds__((2 * 4 * 64 / CW + 3) * 32, 1)
 k_ortho_umma(const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_av,
              const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_vout,
@@ -458,7 +466,7 @@ k_ortho_umma(const __grid_constant__ CUtensorMap map_v, const __grid_constant__ 
                 const uint32_t rsw = ((uint32_t)row >> 1) & 3u;
                 for (int t = 0; t < my; t++) {
                         const int s = t % S, b = t & 1;
-                        mbar_wait(bar_full + 8 * s, (uint32_t)(t / S) & 1u);               // the tile's bytes (TMA)
+                        mbar_wait<SH>(bar_full + 8 * s, (uint32_t)(t / S) & 1u);           // the tile's bytes (TMA)
                         const uint32_t sb = stage0 + s * OSTAGE_BYTES + row * ROW_BYTES;
                         // base terms first: they do not depend on the products
                         uint4 base[CW / 16], alt[CW / 16];
@@ -468,7 +476,7 @@ k_ortho_umma(const __grid_constant__ CUtensorMap map_v, const __grid_constant__ 
                                 if (half == 0) { base[c] = lds128(sb + off); alt[c] = lds128(sb + OT_BYTES + off); }
                                 else { base[c] = lds128(sb + 2 * OT_BYTES + off); alt[c] = make_uint4(0, 0, 0, 0); }
                         }
-                        mbar_wait(bar_acc_full + 8 * b, ((uint32_t)t >> 1) & 1u);          // its products
+                        mbar_wait<SH>(bar_acc_full + 8 * b, ((uint32_t)t >> 1) & 1u);      // its products
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         uint32_t r[CW];
                         tmem_ld_cols<CW>(r, tmem + ((uint32_t)(q * 32) << 16) + b * 128 + half * 64 + col0);
@@ -560,6 +568,10 @@ void dense_umma_prepare(int np)
         cudaFuncSetAttribute(k_ortho_umma<64, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ortho_smem(7));
         cudaFuncSetAttribute(k_ortho_umma<32, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ortho_smem(5));
         cudaFuncSetAttribute(k_ortho_umma<32, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ortho_smem(7));
+        cudaFuncSetAttribute(k_ortho_umma<64, 5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ortho_smem(5));
+        cudaFuncSetAttribute(k_ortho_umma<64, 7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ortho_smem(7));
+        cudaFuncSetAttribute(k_ortho_umma<32, 5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ortho_smem(5));
+        cudaFuncSetAttribute(k_ortho_umma<32, 7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ortho_smem(7));
 }
 
 // wide < 0: follow BLK_DENSE
@@ -579,7 +591,8 @@ int launch_dots_umma(int np, const ModP &m, int64_t rows, const u32 *v, const u3
         return 1;
 }
 
-// variant: 0..3 = (8 epilogue warps, 5 tiles in flight), (8, 7), (16, 5), (16, 7); < 0: the default
+// variant: 0..3 = (8 epilogue warps, 5 tiles in flight), (8, 7), (16, 5), (16, 7); 4..7 = the same with a
+// suspend-time hint on the epilogue waits (not yet measured); < 0: the default
 int launch_ortho_umma(int np, const ModP &m, int64_t rows, u32 *v, const u32 *Av, u32 *p, u32 *v_out, u32 *p_out,
                       const u32 *mats, const DevSmall *state, int force, cudaStream_t st, int variant)
 {
@@ -595,7 +608,11 @@ int launch_ortho_umma(int np, const ModP &m, int64_t rows, u32 *v, const u32 *Av
         case 0: k_ortho_umma<64, 5><<<grid, 11 * 32, ortho_smem(5), st>>>(mv, ma, mp, mvo, mpo, ntile, mats, m, state, force); break;
         case 1: k_ortho_umma<64, 7><<<grid, 11 * 32, ortho_smem(7), st>>>(mv, ma, mp, mvo, mpo, ntile, mats, m, state, force); break;
         case 2: k_ortho_umma<32, 5><<<grid, 19 * 32, ortho_smem(5), st>>>(mv, ma, mp, mvo, mpo, ntile, mats, m, state, force); break;
-        default: k_ortho_umma<32, 7><<<grid, 19 * 32, ortho_smem(7), st>>>(mv, ma, mp, mvo, mpo, ntile, mats, m, state, force); break;
+        case 3: k_ortho_umma<32, 7><<<grid, 19 * 32, ortho_smem(7), st>>>(mv, ma, mp, mvo, mpo, ntile, mats, m, state, force); break;
+        case 4: k_ortho_umma<64, 5, true><<<grid, 11 * 32, ortho_smem(5), st>>>(mv, ma, mp, mvo, mpo, ntile, mats, m, state, force); break;
+        case 5: k_ortho_umma<64, 7, true><<<grid, 11 * 32, ortho_smem(7), st>>>(mv, ma, mp, mvo, mpo, ntile, mats, m, state, force); break;
+        case 6: k_ortho_umma<32, 5, true><<<grid, 19 * 32, ortho_smem(5), st>>>(mv, ma, mp, mvo, mpo, ntile, mats, m, state, force); break;
+        default: k_ortho_umma<32, 7, true><<<grid, 19 * 32, ortho_smem(7), st>>>(mv, ma, mp, mvo, mpo, ntile, mats, m, state, force); break;
         }
         return 1;
 }

@@ -190,7 +190,7 @@ static int test_ortho(const std::vector<int64_t> &sizes)
                         launch_ortho_mma(16, m, rows, v, Av, p, vo[0], po[0], mats, nullptr, 1, 0);
                         CK(cudaDeviceSynchronize());
                         printf(" ortho rows %lld p %u\n", (long long)rows, m.p);
-                        for (int var = 0; var < 4; var++) {
+                        for (int var = 0; var < 8; var++) {
                                 CK(cudaMemset(vo[1], 0xcd, rows * 64)); CK(cudaMemset(po[1], 0xcd, rows * 64));
                                 if (launch_ortho_umma(16, m, rows, v, Av, p, vo[1], po[1], mats, nullptr, 1, 0, var) != 1) { printf("FAIL launch_ortho_umma refused\n"); return 1; }
                                 cudaError_t e = cudaDeviceSynchronize();
@@ -200,7 +200,7 @@ static int test_ortho(const std::vector<int64_t> &sizes)
                                 snprintf(what, sizeof what, "variant %d new p", var); bad += !diff(what, po[0], po[1], rows);
                         }
                         if (pi == 0 && rows >= 1000000) {
-                                for (int which = -1; which < 4; which++) {
+                                for (int which = -1; which < 8; which++) {
                                         float best = 1e9f;
                                         for (int rep = 0; rep < 5; rep++) {
                                                 CK(cudaEventRecord(e0));
@@ -210,7 +210,8 @@ static int test_ortho(const std::vector<int64_t> &sizes)
                                                 float ms = time_ms(e0, e1);
                                                 if (rep && ms < best) best = ms;
                                         }
-                                        const char *names[5] = {"IMMA", "tcgen05 8 epilogue warps, 5 tiles", "tcgen05 8 warps, 7 tiles", "tcgen05 16 warps, 5 tiles", "tcgen05 16 warps, 7 tiles"};
+                                        const char *names[9] = {"IMMA", "tcgen05 8 epilogue warps, 5 tiles", "tcgen05 8 warps, 7 tiles", "tcgen05 16 warps, 5 tiles", "tcgen05 16 warps, 7 tiles",
+                                                                 "8 warps, 5 tiles, suspend hint", "8 warps, 7 tiles, suspend hint", "16 warps, 5 tiles, suspend hint", "16 warps, 7 tiles, suspend hint"};
                                         printf("    %-36s %.3f ms  (%.0f GB/s of 3 reads + 2 writes)\n", names[which + 1], best, rows * 320.0 / best * 1e-6);
                                 }
                         }
