@@ -326,7 +326,10 @@ int dots_num_blocks(int64_t rows, int np)
 int launch_dots(const Geometry &geo, const ModP &m, int64_t rows, const u32 *v, const u32 *Av,
                 u64 *sums, int nblocks, const DevSmall *state, const SmallFuse &fuse, cudaStream_t st)
 {
-        if (dense_umma_supported(geo.np, rows)) return launch_dots_umma(geo.np, m, rows, v, Av, sums, state, fuse, st);
+        if (dense_umma_supported(geo.np, rows)) {
+                int k = launch_dots_umma(geo.np, m, rows, v, Av, sums, state, fuse, st);
+                if (k > 0) return k;          // (a tensor map that cannot be encoded falls through to mma.sync)
+        }
         if (dense_mma_supported(geo.np)) return launch_dots_mma(geo.np, m, rows, v, Av, sums, state, fuse, st);
         switch (geo.np) {
         case 1: return dots_fold<1>(m, rows, v, Av, sums, nblocks, state, fuse, st);
@@ -351,8 +354,10 @@ int launch_small(const Geometry &geo, const ModP &m, u64 *sums, u32 *mats, DevSm
 int launch_ortho(const Geometry &geo, const ModP &m, int64_t rows, u32 *v, const u32 *Av, u32 *p,
                  u32 *v_out, u32 *p_out, const u32 *mats, const DevSmall *state, int force, cudaStream_t st)
 {
-        if (rows > 0 && dense_umma_supported(geo.np, rows))
-                return launch_ortho_umma(geo.np, m, rows, v, Av, p, v_out, p_out, mats, state, force, st);
+        if (rows > 0 && dense_umma_supported(geo.np, rows)) {
+                int k = launch_ortho_umma(geo.np, m, rows, v, Av, p, v_out, p_out, mats, state, force, st);
+                if (k > 0) return k;
+        }
         if (rows >= 0 && dense_mma_supported(geo.np))
                 return launch_ortho_mma(geo.np, m, rows, v, Av, p, v_out, p_out, mats, state, force, st);
         switch (geo.np) {
