@@ -131,6 +131,19 @@ struct blk_ctx {
         std::vector<cudaEvent_t> ev_copies;
         u64 *barrier_word = nullptr;
         ncclResult_t (*nccl_allgather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+        // column-blocked products (experimental, BLK_COLBLOCKS=K; see ColOps below): the consumer of a pieced
+        // exchange starts on the columns whose piece has arrived instead of waiting for the whole vector
+        int colblocks = 0;
+        struct ColOps {
+                int K = 0;
+                std::vector<SpOp> col;           // [K-1] all local rows x the columns of input piece q (of every rank)
+                std::vector<SpOp> last;          // [K]   output row piece i x the columns of input piece K-1
+                std::vector<int64_t> prow;       // [K+1] local row boundaries of the output pieces
+        } cb1, cb2;
+        u32 *zbuf = nullptr;                     // K partial results of one product, zstride elements apart
+        size_t zstride = 0;
+        std::vector<cudaEvent_t> ev_arrived;     // [2K] piece q of tmp (0..K-1) / of Av (K..2K-1) has landed on this rank
+        cudaEvent_t ev_aux = nullptr;
         // loop bookkeeping
         int iters = 0, stopped = 0;
         bool tmp_is_spmv = false;               // tmp rows [0,Mc) hold S1*v of the current v (stop case)
@@ -258,6 +271,48 @@ __global__ void k_select_range(int64_t nnz, const int32_t *__restrict__ key, con
 
 inline unsigned nb(int64_t n) { return (unsigned)((n + 255) / 256); }
 
+// ---- column-blocked products -------------------------------------------------------------------
+// Piece q of rank r along a dimension with block boundaries off[]: rows off[r] + len_r*q/K .. off[r] + len_r*(q+1)/K.
+// The same formula gives the output pieces of the product that writes the dimension and the input pieces of the
+// product that reads it, on every rank, without any exchange.
+static inline int64_t piece_bound(const std::vector<int64_t> &off, int r, int q, int K)
+{
+        return off[r] + (off[r + 1] - off[r]) * q / K;
+}
+
+// select the entries with row key in [rlo, rhi) whose column key lies in piece q of some rank
+// (cb[r*(K+1) + q] <= c < cb[r*(K+1) + q + 1]); okey == nullptr: count only
+__global__ void k_select_colblock(int64_t count, const int32_t *__restrict__ rkey, const int32_t *__restrict__ ckey,
+                                  const u32 *__restrict__ val, int64_t rlo, int64_t rhi, int W, int K, int q,
+                                  const int64_t *__restrict__ cb, int32_t *__restrict__ okey, int32_t *__restrict__ ocol,
+                                  u32 *__restrict__ oval, unsigned long long *__restrict__ counter)
+{
+        int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (s >= count) return;
+        int64_t r = rkey[s], c = ckey[s];
+        if (r < rlo || r >= rhi) return;
+        bool in = false;
+        for (int w = 0; w < W && !in; w++)
+                in = c >= cb[(size_t)w * (K + 1) + q] && c < cb[(size_t)w * (K + 1) + q + 1];
+        if (!in) return;
+        unsigned long long pos = atomicAdd(counter, 1ull);
+        if (okey) { okey[pos] = (int32_t)r; ocol[pos] = (int32_t)c; oval[pos] = val[s]; }
+}
+
+// y[e] = (z_0[e] + ... + z_{K-1}[e]) mod p
+__global__ void k_combine_blocks(u32 *__restrict__ y, const u32 *__restrict__ z, int K, size_t stride, int64_t count, ModP m,
+                                 const DevSmall *__restrict__ state)
+{
+        if (state && state->halt) return;
+        for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x) {
+                u64 acc = 0;
+                for (int q = 0; q < K; q++) acc += z[(size_t)q * stride + e];
+                y[e] = mp_reduce(acc, m);
+        }
+}
+
+
+
 // flags[0] |= any element non-zero; flags[1] |= any element >= p
 __global__ void k_scan_block(const u32 *__restrict__ a, int64_t count, u32 p, int *__restrict__ flags)
 {
@@ -359,6 +414,97 @@ int pushes_done(blk_ctx *c)
         return 0;
 }
 
+// Build the column-blocked form of one product.  rkey/ckey/val: `count` entries on the device (global
+// indices, a superset of this rank's rows); [lo, hi): this rank's output rows; cols: stored length of the
+// input vector; in_off: block boundaries of the input dimension.  Block q < K-1 covers all local rows and
+// the columns of input piece q of every rank; the last column block is cut into K output row pieces, so
+// that output piece i is final -- and can travel -- as soon as its slice of the last block is done.
+int build_colops(blk_ctx *c, blk_ctx::ColOps *ops, int K, int chunk_len, int64_t count, const int32_t *rkey,
+                 const int32_t *ckey, const u32 *val, int64_t lo, int64_t hi, int64_t cols, const std::vector<int64_t> &in_off)
+{
+        const int W = c->world;
+        ops->K = K;
+        ops->col.assign((size_t)K - 1, SpOp());
+        ops->last.assign((size_t)K, SpOp());
+        ops->prow.assign((size_t)K + 1, 0);
+        for (int i = 0; i <= K; i++) ops->prow[i] = (hi - lo) * i / K;
+        std::vector<int64_t> hb((size_t)W * (K + 1));
+        for (int r = 0; r < W; r++)
+                for (int q = 0; q <= K; q++) hb[(size_t)r * (K + 1) + q] = piece_bound(in_off, r, q, K);
+        int64_t *db = nullptr;
+        unsigned long long *cnt = nullptr;
+        CU(cudaMalloc(&db, sizeof(int64_t) * hb.size()));
+        CU(cudaMalloc(&cnt, sizeof(unsigned long long)));
+        CU(cudaMemcpyAsync(db, hb.data(), sizeof(int64_t) * hb.size(), cudaMemcpyHostToDevice, c->stream));
+        int rc = 0;
+        auto one = [&](SpOp *op, int q, int64_t rlo, int64_t rhi) -> int {
+                unsigned long long h = 0;
+                int32_t *sr = nullptr, *sc = nullptr;
+                u32 *sx = nullptr;
+                CU(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
+                if (count) k_select_colblock<<<nb(count), 256, 0, c->stream>>>(count, rkey, ckey, val, rlo, rhi, W, K, q, db, nullptr, nullptr, nullptr, cnt);
+                CU(cudaMemcpyAsync(&h, cnt, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+                CU(cudaStreamSynchronize(c->stream));
+                const size_t cap = h ? (size_t)h : 1;
+                CU(cudaMalloc(&sr, sizeof(int32_t) * cap));
+                CU(cudaMalloc(&sc, sizeof(int32_t) * cap));
+                CU(cudaMalloc(&sx, sizeof(u32) * cap));
+                CU(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
+                if (count) k_select_colblock<<<nb(count), 256, 0, c->stream>>>(count, rkey, ckey, val, rlo, rhi, W, K, q, db, sr, sc, sx, cnt);
+                CU(cudaStreamSynchronize(c->stream));
+                std::string err = build_operator(op, c->geo, chunk_len, rhi - rlo, cols, rlo, (int64_t)h, sr, sc, sx, c->m.p,
+                                                 nullptr, nullptr, 1, c->stream);
+                cudaFree(sr); cudaFree(sc); cudaFree(sx);
+                if (!err.empty()) return fail("column block: " + err);
+                return 0;
+        };
+        for (int q = 0; q < K - 1 && !rc; q++)
+                if (hi > lo) rc = one(&ops->col[q], q, lo, hi);
+        for (int i = 0; i < K && !rc; i++)
+                if (ops->prow[i + 1] > ops->prow[i]) rc = one(&ops->last[i], K - 1, lo + ops->prow[i], lo + ops->prow[i + 1]);
+        cudaFree(db); cudaFree(cnt);
+        return rc;
+}
+
+void free_colops(blk_ctx::ColOps *ops)
+{
+        for (auto &o : ops->col) free_operator(&o);
+        for (auto &o : ops->last) free_operator(&o);
+        ops->col.clear(); ops->last.clear(); ops->K = 0;
+}
+
+// y (local rows) <- S x through the column blocks.  arrived[q] (nullable array) gates column block q;
+// before_last() runs after the first K-1 blocks; after_piece(i) runs when output rows prow[i] .. prow[i+1] are final.  Returns the kernels launched, < 0 on error.
+template <class B, class F>
+int colblock_product(blk_ctx *c, blk_ctx::ColOps &ops, const u32 *x, u32 *y, const DevSmall *state, cudaEvent_t *arrived,
+                     B before_last, F after_piece)
+{
+        const int K = ops.K, np = c->geo.np;
+        int k = 0;
+        for (int q = 0; q < K - 1; q++) {
+                if (arrived && cudaStreamWaitEvent(c->stream, arrived[q], 0) != cudaSuccess) return -1;
+                if (ops.col[q].rows > 0) k += launch_spmv(ops.col[q], c->geo, c->m, x, c->zbuf + (size_t)q * c->zstride, state, c->stream);
+        }
+        {
+                int kb = before_last();        // work that must precede the first finished piece (returns kernels launched)
+                if (kb < 0) return -1;
+                k += kb;
+        }
+        if (arrived && cudaStreamWaitEvent(c->stream, arrived[K - 1], 0) != cudaSuccess) return -1;
+        for (int i = 0; i < K; i++) {
+                const int64_t lo = ops.prow[i], hi = ops.prow[i + 1];
+                if (hi > lo) {
+                        k += launch_spmv(ops.last[i], c->geo, c->m, x, c->zbuf + (size_t)(K - 1) * c->zstride + (size_t)lo * np, state, c->stream);
+                        const int64_t cnt = (hi - lo) * np;
+                        unsigned blocks = (unsigned)std::min<int64_t>(148 * 8, (cnt + 255) / 256);
+                        k_combine_blocks<<<blocks, 256, 0, c->stream>>>(y + (size_t)lo * np, c->zbuf + (size_t)lo * np, K, c->zstride, cnt, c->m, state);
+                        k += 1;
+                }
+                if (after_piece(i)) return -1;
+        }
+        return k;
+}
+
 // Multi-GPU iteration.  Invariant at entry: tmp (full length, on every rank) = S1 v for the current
 // v, Tp (local rows) = S1 p.  Because S1 is linear and the n x n factors act on the right,
 //     S1 v' = sel(d, S1 Av, S1 v) + (S1 v) c + (S1 p) vtAvd,      S1 p' = sel(d, 0, S1 p) + (S1 v) winv
@@ -453,6 +599,87 @@ int enqueue_iteration_mg(blk_ctx *c, EventTimer *tm)
         return 0;
 }
 
+// Multi-GPU iteration with column-blocked consumers (BLK_COLBLOCKS=K, experimental; not yet measured).
+// Same invariant and recurrence as enqueue_iteration_mg.  What changes is when work may start: a product
+// begins with the column blocks whose input pieces have already landed, so the exchange of one product's
+// result also hides behind the first K-1 blocks of the next product, and a product's last column block is
+// computed in output-row pieces that are broadcast one by one.  Nothing on the main stream waits for a whole
+// exchange except the n x n stage (its all-reduce is queued behind the Av broadcasts on the communicator's stream).
+int enqueue_iteration_mg_arrival(blk_ctx *c, EventTimer *tm)
+{
+        const Geometry &g = c->geo;
+        const int np = g.np, K = c->colblocks;
+        const int64_t lrows = c->n1() - c->n0();
+        u32 *vloc = c->v + (size_t)c->n0() * np;
+        u32 *tloc = c->tmp + (size_t)c->m0() * np;
+        cudaEvent_t *tmp_in = c->ev_arrived.data(), *av_in = tmp_in + K;
+        auto nothing = []() -> int { return 0; };
+
+        // Av <- S2 tmp
+        if (tm) tm->begin(c, BLK_PH_SPMV2);
+        int k = colblock_product(c, c->cb2, c->tmp, c->Av, c->state, tmp_in, nothing, [&](int i) -> int {
+                CU(cudaEventRecord(c->ev_piece[i], c->stream));
+                CU(cudaStreamWaitEvent(c->comm_stream, c->ev_piece[i], 0));
+                if (piece_broadcast(c, c->Av_full, c->n_off, c->piece_rows_all2, K, i, c->comm_stream)) return 1;
+                CU(cudaEventRecord(av_in[i], c->comm_stream));
+                return 0;
+        });
+        if (k < 0) return g_err.empty() ? fail("column-blocked product 2") : 1;
+        c->launches += k;
+        if (tm) tm->end(c, k);
+
+        if (tm) tm->begin(c, BLK_PH_DOTS);
+        k = launch_dots(g, c->m, lrows, vloc, c->Av, c->sums, c->dots_blocks, c->state, SmallFuse(), c->stream);
+        c->launches += k;
+        if (tm) tm->end(c, k);
+        CU(cudaEventRecord(c->ev_aux, c->stream));
+        CU(cudaStreamWaitEvent(c->comm_stream, c->ev_aux, 0));
+        NC(g_nccl.AllReduce(c->sums, c->sums, (size_t)2 * np * np, ncclUint64, ncclSum, c->comm, c->comm_stream));
+        CU(cudaEventRecord(c->ev_comm, c->comm_stream));
+
+        // U <- S1 Av, then tmp <- orthogonalize(tmp, U, Tp) piece by piece (the recurrence), each piece broadcast at once
+        if (tm) tm->begin(c, BLK_PH_SPMV1);
+        k = colblock_product(c, c->cb1, c->Av_full, c->U, nullptr, av_in,
+                [&]() -> int {
+                        // the n x n stage needs the all-reduce, which sits behind the last Av broadcast
+                        if (cudaStreamWaitEvent(c->stream, c->ev_comm, 0) != cudaSuccess) return -1;
+                        int kk = launch_small(g, c->m, c->sums, c->mats, c->state, 0, c->stream);
+                        kk += launch_ortho(g, c->m, lrows, vloc, c->Av, c->p, vloc, c->p, c->mats, c->state, 0, c->stream);
+                        if (c->tmp_prev &&
+                            cudaMemcpyAsync(c->tmp_prev, tloc, sizeof(u32) * (size_t)(c->m1() - c->m0()) * np, cudaMemcpyDeviceToDevice,
+                                            c->stream) != cudaSuccess)
+                                return -1;
+                        return kk;
+                },
+                [&](int i) -> int {
+                        const int64_t lo = c->cb1.prow[i], hi = c->cb1.prow[i + 1];
+                        if (hi > lo)
+                                c->launches += launch_ortho(g, c->m, hi - lo, tloc + (size_t)lo * np, c->U + (size_t)lo * np, c->Tp + (size_t)lo * np,
+                                                            tloc + (size_t)lo * np, c->Tp + (size_t)lo * np, c->mats, c->state, 0, c->stream);
+                        CU(cudaEventRecord(c->ev_piece[i], c->stream));
+                        CU(cudaStreamWaitEvent(c->comm_stream, c->ev_piece[i], 0));
+                        if (piece_broadcast(c, c->tmp, c->m_off, c->piece_rows_all, K, i, c->comm_stream)) return 1;
+                        CU(cudaEventRecord(tmp_in[i], c->comm_stream));
+                        return 0;
+                });
+        if (k < 0) return g_err.empty() ? fail("column-blocked product 1") : 1;
+        c->launches += k;
+        if (tm) tm->end(c, k);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(e));
+        return 0;
+}
+
+// the exchange of the last pieces may still be running on the communicator's stream
+int drain_exchange(blk_ctx *c)
+{
+        if (c->colblocks && c->comm_stream) {
+                CU(cudaEventRecord(c->ev_comm, c->comm_stream));
+                CU(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
+        }
+        return 0;
+}
+
 // establish the invariant of enqueue_iteration_mg from v (full, on every rank) and p_full (may be null)
 int mg_prepare(blk_ctx *c, const u32 *p_full_dev)
 {
@@ -471,7 +698,7 @@ int mg_prepare(blk_ctx *c, const u32 *p_full_dev)
 // one iteration of the loop body, sequential/lanczos_modp.c:635-656
 int enqueue_iteration(blk_ctx *c, EventTimer *tm)
 {
-        if (c->mg_recur) return enqueue_iteration_mg(c, tm);
+        if (c->mg_recur) return c->colblocks ? enqueue_iteration_mg_arrival(c, tm) : enqueue_iteration_mg(c, tm);
         const Geometry &g = c->geo;
         const int np = g.np;
         int k;
@@ -498,7 +725,11 @@ int enqueue_iteration(blk_ctx *c, EventTimer *tm)
                 CU(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
                 if (tm) tm->end(c, 0);
         } else {
-                k = launch_spmv(c->S1, g, c->m, c->v, c->tmp + (size_t)c->m0() * np, c->state, c->stream);
+                if (c->colblocks && c->world == 1) {
+                        k = colblock_product(c, c->cb1, c->v, c->tmp, c->state, nullptr, []() -> int { return 0; }, [](int) -> int { return 0; });
+                        if (k < 0) return fail("column-blocked product 1");
+                } else
+                        k = launch_spmv(c->S1, g, c->m, c->v, c->tmp + (size_t)c->m0() * np, c->state, c->stream);
                 c->launches += k;
                 if (tm) tm->end(c, k);
                 if (c->world > 1) {
@@ -508,7 +739,11 @@ int enqueue_iteration(blk_ctx *c, EventTimer *tm)
                 }
         }
         if (tm) tm->begin(c, BLK_PH_SPMV2);
-        k = launch_spmv(c->S2, g, c->m, c->tmp, c->Av, c->state, c->stream);
+        if (c->colblocks && c->world == 1) {
+                k = colblock_product(c, c->cb2, c->tmp, c->Av, c->state, nullptr, []() -> int { return 0; }, [](int) -> int { return 0; });
+                if (k < 0) return fail("column-blocked product 2");
+        } else
+                k = launch_spmv(c->S2, g, c->m, c->tmp, c->Av, c->state, c->stream);
         c->launches += k;
         if (tm) tm->end(c, k);
 
@@ -713,6 +948,10 @@ int blk_destroy(blk_ctx *c)
         if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
         free_operator(&c->S1);
         free_operator(&c->S2);
+        free_colops(&c->cb1); free_colops(&c->cb2);
+        cudaFree(c->zbuf);
+        for (auto e : c->ev_arrived) cudaEventDestroy(e);
+        if (c->ev_aux) cudaEventDestroy(c->ev_aux);
         cudaFree(c->v); cudaFree(c->tmp); cudaFree(c->p);
         if (c->Av_full) cudaFree(c->Av_full); else cudaFree(c->Av);
         cudaFree(c->Tp); cudaFree(c->U); cudaFree(c->tmp_prev);
@@ -762,6 +1001,14 @@ int blk_create(blk_ctx **out, const blk_params *prm)
         c->N = c->right ? prm->ncols : prm->nrows;
         c->Mc = c->right ? prm->nrows : prm->ncols;
         c->use_graph = prm->use_graph;
+        {
+                // experimental: column-blocked products (world == 1: a test mode that exercises the blocks and the
+                // combine kernel under the whole single-GPU test suite; world > 1: arrival-order exchange)
+                const char *e = getenv("BLK_COLBLOCKS");
+                int K = e ? atoi(e) : 0;
+                const char *er = getenv("BLK_RECUR"), *ep = getenv("BLK_P2P");
+                if (K >= 2 && K <= 16 && !(world > 1 && ((er && er[0] == '0') || (ep && ep[0] == '1')))) c->colblocks = K;
+        }
         const int np = c->geo.np;
 #define CUX(call)                                                                                  \
         do {                                                                                       \
@@ -824,7 +1071,7 @@ int blk_create(blk_ctx **out, const blk_params *prm)
                 CUX(cudaGetDeviceProperties(&prop, c->device));
                 long long min_bytes = emin ? atoll(emin) : 96ll << 20;
                 long long hot_bytes = eb ? atoll(eb) : 24ll << 20;
-                bool on = world == 1 && !(e && e[0] == '0') && np >= 4 && nnz > 0 &&
+                bool on = world == 1 && !c->colblocks && !(e && e[0] == '0') && np >= 4 && nnz > 0 &&
                           (long long)c->N * np * 4 > min_bytes && hot_bytes > 0;
                 if (on) {
                         std::string err = degree_sort_maps(nnz, idxN, c->N, &c->n_old2new, &c->n_new2old, c->stream);
@@ -860,6 +1107,11 @@ int blk_create(blk_ctx **out, const blk_params *prm)
                         err = build_operator(op, c->geo, prm->chunk_len, hi - lo, cols, lo, nnz, rk, ck, dx, m.p,
                                              which ? c->n_old2new : nullptr, which ? nullptr : c->n_old2new, 1, c->stream);
                         if (!which) op->hot_cols = (u32)c->hot_rows;
+                        if (err.empty() && c->colblocks &&
+                            build_colops(c, which ? &c->cb2 : &c->cb1, c->colblocks, prm->chunk_len, nnz, rk, ck, dx, lo, hi, cols,
+                                         which ? c->m_off : c->n_off)) {
+                                free_coo(); blk_destroy(c); return 1;
+                        }
                 } else {
                         int32_t *sr = nullptr, *sc = nullptr; u32 *sx = nullptr;
                         unsigned long long *cnt = nullptr, hcnt = 0;
@@ -889,6 +1141,12 @@ int blk_create(blk_ctx **out, const blk_params *prm)
                         if ((int64_t)hcnt != sel) err = "shard selection count mismatch";
                         else err = build_operator(op, c->geo, prm->chunk_len, hi - lo, cols, lo, sel, sr, sc, sx, m.p, nullptr, nullptr,
                                                        want_pieces, c->stream);
+                        if (err.empty() && c->colblocks &&
+                            build_colops(c, which ? &c->cb2 : &c->cb1, c->colblocks, prm->chunk_len, sel, sr, sc, sx, lo, hi, cols,
+                                         which ? c->m_off : c->n_off)) {
+                                cudaFree(sr); cudaFree(sc); cudaFree(sx);
+                                free_coo(); blk_destroy(c); return 1;
+                        }
                         cudaFree(sr); cudaFree(sc); cudaFree(sx);
                 }
                 if (!err.empty()) { free_coo(); fail(err); blk_destroy(c); return 1; }
@@ -905,6 +1163,13 @@ int blk_create(blk_ctx **out, const blk_params *prm)
         CUX(cudaMemsetAsync(c->v, 0, bv, c->stream)); CUX(cudaMemsetAsync(c->tmp, 0, bt, c->stream));
         CUX(cudaMemsetAsync(c->Av, 0, bl, c->stream)); CUX(cudaMemsetAsync(c->p, 0, bl, c->stream));
         c->block_bytes = bv + bt + 2 * bl;
+        if (c->colblocks) {
+                int64_t lm_ = c->m1() - c->m0();
+                c->zstride = (size_t)std::max<int64_t>(1, std::max(ln, lm_)) * np;
+                CUX(cudaMalloc(&c->zbuf, sizeof(u32) * c->zstride * c->colblocks));
+                CUX(cudaMemsetAsync(c->zbuf, 0, sizeof(u32) * c->zstride * c->colblocks, c->stream));
+                c->block_bytes += sizeof(u32) * c->zstride * c->colblocks;
+        }
         c->dots_blocks = dots_num_blocks(ln, np);
         CUX(cudaMalloc(&c->mats, sizeof(u32) * mats_words(np)));
         CUX(cudaMalloc(&c->sums, sizeof(u64) * (size_t)2 * np * np));
@@ -970,6 +1235,21 @@ int blk_create(blk_ctx **out, const blk_params *prm)
                                 const std::vector<int64_t> &off = which ? c->n_off : c->m_off;
                                 for (int r = 0; r < world; r++) dst[(size_t)r * 2 + 1] = off[r + 1] - off[r];
                         }
+                }
+                if (c->colblocks) {
+                        // arrival-order mode: pieces are equal row counts, known on every rank without an exchange
+                        const int K = c->colblocks;
+                        c->pieces = c->pieces2 = K;
+                        c->piece_rows_all.assign((size_t)world * (K + 1), 0);
+                        c->piece_rows_all2.assign((size_t)world * (K + 1), 0);
+                        for (int r = 0; r < world; r++)
+                                for (int q = 0; q <= K; q++) {
+                                        c->piece_rows_all[(size_t)r * (K + 1) + q] = (c->m_off[r + 1] - c->m_off[r]) * q / K;
+                                        c->piece_rows_all2[(size_t)r * (K + 1) + q] = (c->n_off[r + 1] - c->n_off[r]) * q / K;
+                                }
+                        c->ev_arrived.resize((size_t)2 * K);
+                        for (auto &ev : c->ev_arrived) CUX(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                        CUX(cudaEventCreateWithFlags(&c->ev_aux, cudaEventDisableTiming));
                 }
                 {
                         // highest priority: the block scheduler then places NCCL's few large CTAs ahead
@@ -1099,7 +1379,7 @@ int blk_iterate(blk_ctx *c, int32_t max_iters, int32_t *iters_total, int32_t *st
                 c->h_state->stopped = 0; c->h_state->halt = 0; c->h_state->do_ortho = 0;
                 if (push_state(c)) return 1;
                 bool graph = c->use_graph == 1 || (c->use_graph < 0 && c->world == 1 && max_iters >= 4);
-                if (c->profiling || c->world > 1) graph = false;
+                if (c->profiling || c->world > 1 || c->colblocks) graph = false;
                 EventTimer tm;
                 int done = 0;
                 if (graph && !c->graph) {
@@ -1120,6 +1400,7 @@ int blk_iterate(blk_ctx *c, int32_t max_iters, int32_t *iters_total, int32_t *st
                                         if (enqueue_iteration(c, c->profiling ? &tm : nullptr)) return 1;
                         }
                         done += batch;
+                        if (drain_exchange(c)) return 1;
                         if (pull_state(c)) return 1;
                         if (c->profiling) tm.resolve(c);
                         if (c->h_state->halt) break;

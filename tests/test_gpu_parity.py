@@ -6,6 +6,8 @@ run-time self checks): per-function comparison on seeded in
 in-loop invariants of correctness_tests (sequential/lanczos_modp.c:532-557), final_check
 (:560-582) and the checker_modp property x*M == 0.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -316,3 +318,26 @@ def test_device_side_final_check_and_checker(lib, oracle):
         big = V.copy(); big[3] = p                                  # entry >= p is rejected
         assert not ctx.check_kernel_block(big)
         assert not oracle.sparse_matrix_vector_product(M, V, True, n, p).any()
+
+
+@pytest.mark.skipif(not os.environ.get("BLK_TEST_EXPERIMENTAL"), reason="experimental path: set BLK_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("K", [2, 3, 5])
+def test_column_blocked_products_single_gpu(lib, oracle, monkeypatch, K):
+    """BLK_COLBLOCKS=K on one GPU: every product runs as K-1 column blocks over all rows plus a last column
+    block cut into K row pieces, summed mod p by the combine kernel (the building blocks of the arrival-order
+    multi-GPU exchange, context.cu).  Whole runs must stay bit-identical to the oracle."""
+    monkeypatch.setenv("BLK_COLBLOCKS", str(K))
+    s = lib.synth
+    cases = [(s.powerlaw_rows(900, 800, mean=7, seed=2, with_empty_rows=40, order="file"), 4, P_FERMAT, False, -1),
+             (s.uniform_nnz(2500, 3100, 30000, seed=4, order="col"), 16, P_MERSENNE, True, 9),
+             (s.powerlaw_rows(1200, 1500, mean=7, seed=6), 5, P_CAP, False, 6),
+             (s.uniform_rows(7, 9, 2, seed=1), 2, P_FERMAT, False, 3)]           # fewer rows than blocks
+    for M, n, p, right, stop_after in cases:
+        Mp = M.reduced(p)
+        N = M.ncols if right else M.nrows
+        with lib.BlockLanczos(Mp, n=n, prime=p, right=right) as ctx:
+            got = ctx.block_lanczos(oracle.start_block(N * n, p), stop_after=stop_after, batch=4)
+        want = oracle.lanczos_run(Mp, n, p, right, stop_after=stop_after)
+        assert got["iters"] == want["iters"] and got["stopped"] == want["stopped"]
+        for k in ("v", "tmp", "Av", "p"):
+            assert np.array_equal(got[k], want[k]), (K, n, k)
