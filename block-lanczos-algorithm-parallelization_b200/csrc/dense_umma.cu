@@ -509,16 +509,16 @@ typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, 
 
 EncodeTiled encode_fn()
 {
-        static EncodeTiled fn = nullptr;
-        static bool tried = false;
-        if (!tried) {
-                tried = true;
+        // resolved once; initialisation of a function-local static is thread-safe (one context per thread
+        // in a multi-GPU process, tools/mg_check.cu)
+        static const EncodeTiled fn = []() -> EncodeTiled {
                 void *p = nullptr;
                 cudaDriverEntryPointQueryResult qr;
                 if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
                     qr == cudaDriverEntryPointSuccess)
-                        fn = (EncodeTiled)p;
-        }
+                        return (EncodeTiled)p;
+                return nullptr;
+        }();
         return fn;
 }
 
