@@ -7,6 +7,8 @@
 //              system serves monotone-with-gaps traffic near its streaming rate, and both halves of a line are
 //              used when both rows are wanted, the lines fetched per gather drop from 1 to (1 - exp(-2 lam)) / (2 lam) ...
 //              the probe simply reports gathers/s per density.
+//   1b. lockstep: the same with many sweepers advancing through the table TOGETHER, each taking one row per window --
+//              the access pattern of a band whose rows are spread over all warps (accumulators in shared memory).
 //   2. red:    throughput of red.global.add.u64 on an L2-resident accumulator block (rows of 16 u64 = 128 bytes,
 //              random rows), i.e. the price of accumulating y in L2 instead of in registers.
 #include <cstdio>
@@ -47,6 +49,33 @@ k_sweep(const uint4 *__restrict__ tab, uint64_t nrows, uint64_t span, uint32_t t
                 for (int u = 0; u < 8; u++) { acc.x ^= v[u].x; acc.y += v[u].y; acc.z ^= v[u].z; acc.w += v[u].w; mine += take[u] && sub == 0; }
         }
         if (mine) atomicAdd(count, mine);
+        if (acc.x == 0x12345678u && acc.y == 42) out[0] = acc;
+}
+
+// "Lockstep" model of the banded product: S sweepers (4 lanes = one 64-byte row each) advance through the table
+// together; in window k (S * gap consecutive rows) every sweeper gathers exactly one row, at a hashed position, so
+// each sweeper's addresses increase, the union of all sweepers touches 1/gap of the rows, and the two rows of a
+// 128-byte line are wanted by DIFFERENT sweepers at about the same time -- L2 has to provide the sharing.
+// Nothing synchronises the sweepers (drift is part of what is measured).
+__global__ void __launch_bounds__(256)
+k_lockstep(const uint4 *__restrict__ tab, uint64_t nrows, uint64_t S, uint32_t gap, uint64_t steps, uint4 *out)
+{
+        const uint64_t s = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+        const int sub = threadIdx.x & 3;
+        uint4 acc = make_uint4(0, 0, 0, 0);
+        for (uint64_t k0 = 0; k0 < steps; k0 += 8) {
+                uint4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                        const uint64_t k = k0 + u;
+                        const uint64_t slot = (s + mix(k)) % S;                        // a permutation of the sweepers per window
+                        uint64_t r = (k * S + slot) * gap + mix(k * S + slot) % gap;
+                        if (r >= nrows) r = nrows - 1;
+                        v[u] = __ldg(tab + r * 4 + sub);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) { acc.x ^= v[u].x; acc.y += v[u].y; acc.z ^= v[u].z; acc.w += v[u].w; }
+        }
         if (acc.x == 0x12345678u && acc.y == 42) out[0] = acc;
 }
 
@@ -93,6 +122,26 @@ int main()
                 }
                 printf("  density %.2f: %.3f ms  %7.2f G gathers/s  (%.0f GB/s of useful 64 B rows; random gathers: 46.5 G/s)\n", d, best,
                        h / best / 1e6, h * 64.0 / best / 1e6);
+        }
+        // ---- 1b. lockstep sweepers
+        {
+                const uint64_t S = 148ull * 2048 / 4;                     // one sweeper per 4 resident threads
+                printf("lockstep sweepers (%llu lane groups advance through the table together; 1 row in `gap` is gathered)\n", (unsigned long long)S);
+                for (uint32_t gap : {1u, 2u, 3u, 4u, 8u}) {
+                        const uint64_t steps = (nrows / gap / S) & ~7ull;
+                        float best = 1e9f;
+                        for (int rep = 0; rep < 3; rep++) {
+                                CK(cudaEventRecord(a));
+                                k_lockstep<<<(unsigned)(S * 4 / 256), 256>>>(tab, nrows, S, gap, steps, out);
+                                CK(cudaEventRecord(b));
+                                CK(cudaEventSynchronize(b));
+                                float ms; CK(cudaEventElapsedTime(&ms, a, b));
+                                if (ms < best) best = ms;
+                        }
+                        const double gathers = (double)steps * S;
+                        printf("  gap %u: %.3f ms  %7.2f G gathers/s  (%.0f GB/s of useful rows; random gathers: 46.5 G/s)\n", gap, best, gathers / best / 1e6,
+                               gathers * 64.0 / best / 1e6);
+                }
         }
         CK(cudaFree(tab));
         // ---- 2. L2-resident u64 reductions
