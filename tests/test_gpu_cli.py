@@ -146,15 +146,15 @@ def test_cli_wide_matrix_tmp_tail(driver, lib, tmp_path):
 
 @pytest.mark.parametrize("n", [16, 13])
 def test_cli_dense_kernel_families_agree(driver, lib, tmp_path, n):
-    """n_pad = 16 has two tensor-core implementations of the dense phases: tcgen05 + TMA (default;
-    BLK_DENSE=umma64 = its two-instruction variant) and mma.sync int8 (BLK_DENSE=mma).  Whole runs must
-    end in byte-identical kernel files, accepted by the reference's checker."""
+    """n_pad = 16 has two tensor-core implementations of the dense phases: tcgen05 + TMA (default) and
+    mma.sync int8 (BLK_DENSE=mma).  Whole runs must end in byte-identical kernel files, accepted by the
+    reference's checker (tools/umma_cli_check.sh additionally pins both to the reference's own output)."""
     p = 2147483647
     M = lib.synth.powerlaw_rows(2800, 3000, mean=9, seed=21, with_empty_rows=7)      # more columns than rows: a right kernel exists
     mtx = str(tmp_path / "m.mtx")
     lib.synth.write_mtx(mtx, M)
     hashes = {}
-    for mode in ("", "umma64", "mma"):
+    for mode in ("", "mma"):
         out = str(tmp_path / f"k_{mode or 'default'}.mtx")
         env = dict(os.environ)
         env.pop("BLK_DENSE", None)
