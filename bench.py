@@ -167,6 +167,21 @@ def expected_nnz(w):
 
 
 # ------------------------------------------------------------------------------------------
+def dense_roofline(phases_ms_per_step, rows_local, n_pad, peak):
+    """Secondary kernels against the same HBM peak: algorithmic bytes of SURVEY 8(d) (block_dot_products reads v and
+    Av: 2 blocks; orthogonalize reads v, Av, p and writes v, p: 5 blocks of rows x n_pad x 4 bytes) over the in-run
+    phase times.  On one GPU the dots phase includes the fused n x n stage (one block, ~25 us)."""
+    out = {}
+    block = rows_local * n_pad * 4
+    for key, blocks, kernel in (("dots", 2, "block_dot_products (+ n x n stage)"), ("ortho", 5, "orthogonalize")):
+        ms = float(phases_ms_per_step.get(key, 0.0) or 0.0)
+        if ms > 0 and block > 0:
+            ach = blocks * block / (ms * 1e-3) / 1e9
+            out[key] = {"kernel": kernel, "bound": "hbm", "bytes_per_launch": blocks * block, "ms_per_launch": ms,
+                        "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -346,6 +361,10 @@ def main():
             "spmv_gnnzn_per_s": spmv_rate, "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
             "phases_ms_per_step": {k: v["ms"] / a.steps for k, v in phases.items()},
             "setup_s": {"generate": t_gen, "build_layout": t_build}, "device_bytes": info["device_bytes"]}
+    try:
+        line["roofline_dense"] = dense_roofline(line["phases_ms_per_step"], info["local_N1"] - info["local_N0"], info["n_pad"], peak)
+    except Exception as exc:          # secondary information must never cost the bench line
+        line["roofline_dense"] = {"error": str(exc)}
     if e2e:
         line["e2e"] = e2e
 

@@ -33,3 +33,14 @@ def test_non_zero_ranks_of_the_reference_arm_do_nothing():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
                        capture_output=True, text=True, timeout=60, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_dense_roofline_helper():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_bench", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    r = b.dense_roofline({"spmv1": 27.6, "dots": 0.92, "ortho": 2.63, "small": 0.0}, 50_000_000, 16, 6449.0)
+    assert abs(r["dots"]["achieved"] - 2 * 3.2e9 / 0.92e-3 / 1e9) < 1e-6 and 1.0 < r["dots"]["frac"] < 1.2
+    assert abs(r["ortho"]["bytes_per_launch"] - 16e9) < 1 and 0.9 < r["ortho"]["frac"] < 1.0
+    assert b.dense_roofline({}, 10, 16, 6449.0) == {} and b.dense_roofline({"dots": 0.0}, 10, 16, 6449.0) == {}
