@@ -51,6 +51,10 @@ struct NcclApi {
         ncclResult_t (*GroupStart)() = nullptr;
         ncclResult_t (*GroupEnd)() = nullptr;
         const char *(*GetErrorString)(ncclResult_t) = nullptr;
+        // only needed by the P x Q grid mode (BLK_GRID); resolved lazily, may be null
+        ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+        ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+        ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t *, void *) = nullptr;
 };
 NcclApi g_nccl;
 
@@ -73,6 +77,9 @@ bool nccl_load(std::string *why)
         SYM(GroupEnd, "ncclGroupEnd")
         SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
+        *(void **)(&g_nccl.Send) = dlsym(h, "ncclSend");
+        *(void **)(&g_nccl.Recv) = dlsym(h, "ncclRecv");
+        *(void **)(&g_nccl.CommSplit) = dlsym(h, "ncclCommSplit");
         g_nccl.lib = h;
         return true;
 }
@@ -144,6 +151,25 @@ struct blk_ctx {
         size_t zstride = 0;
         std::vector<cudaEvent_t> ev_arrived;     // [2K] piece q of tmp (0..K-1) / of Av (K..2K-1) has landed on this rank
         cudaEvent_t ev_aux = nullptr;
+        // P x Q block grid (experimental, BLK_GRID=PxQ | auto; the reference's 2-D decomposition, blk_plan_grid):
+        // rank (a,b) = a*Q + b holds block (a,b) of the operator in both orientations and owns piece (a,b) of
+        // v, Av, p and piece (b,a) of tmp.  The 1-D operators and blocks above stay in place for everything
+        // outside the loop (get_state, final_check, ...): grid_export() copies the distributed state into them.
+        struct Grid {
+                int P = 0, Q = 0, a = 0, b = 0;
+                std::vector<int64_t> n_off, m_off, n_sub, m_sub;     // as returned by blk_plan_grid
+                int64_t pieceN = 0, pieceM = 0;                      // padded piece rows inside my block row / column
+                int64_t pieceNmax = 0, pieceMmax = 0;                // over all blocks (world-wide gathers)
+                ncclComm_t row_comm = nullptr, col_comm = nullptr;
+                SpOp S1, S2;                                         // (P*pieceM) x (Q*pieceN) and its transpose
+                u32 *vblk = nullptr, *tblk = nullptr;                // v_a (Q pieces), tmp_b (P pieces), piece-padded
+                u32 *part1 = nullptr, *part2 = nullptr;              // partial tmp_b / partial Av_a (separate: a halted iteration
+                                                                     // skips the products and must find its own partial again)
+                u32 *recv = nullptr;                                 // pieces received in a reduce-scatter
+                u32 *Av = nullptr, *p = nullptr;                     // owned piece
+                bool dirty = false;                                  // the 1-D copies are stale
+        } grid;
+        bool grid_on = false;
         // loop bookkeeping
         int iters = 0, stopped = 0;
         bool tmp_is_spmv = false;               // tmp rows [0,Mc) hold S1*v of the current v (stop case)
@@ -297,6 +323,38 @@ __global__ void k_select_colblock(int64_t count, const int32_t *__restrict__ rke
         if (!in) return;
         unsigned long long pos = atomicAdd(counter, 1ull);
         if (okey) { okey[pos] = (int32_t)r; ocol[pos] = (int32_t)c; oval[pos] = val[s]; }
+}
+
+// entries of grid block (a,b) with block-local, piece-padded indices: piece k of the block starts at k*piece rows
+__global__ void k_select_grid(int64_t nnz, const int32_t *__restrict__ iN, const int32_t *__restrict__ iM,
+                              const u32 *__restrict__ val, int Q, const int64_t *__restrict__ nsub, int64_t pieceN, int P,
+                              const int64_t *__restrict__ msub, int64_t pieceM, int32_t *__restrict__ oN,
+                              int32_t *__restrict__ oM, u32 *__restrict__ oval, unsigned long long *__restrict__ counter)
+{
+        int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (s >= nnz) return;
+        const int64_t g = iN[s], h = iM[s];
+        if (g < nsub[0] || g >= nsub[Q] || h < msub[0] || h >= msub[P]) return;
+        int bq = 0, ap = 0;
+        while (bq + 1 < Q && g >= nsub[bq + 1]) bq++;
+        while (ap + 1 < P && h >= msub[ap + 1]) ap++;
+        unsigned long long pos = atomicAdd(counter, 1ull);
+        if (oN) {
+                oN[pos] = (int32_t)(bq * pieceN + (g - nsub[bq]));
+                oM[pos] = (int32_t)(ap * pieceM + (h - msub[ap]));
+                oval[pos] = val[s];
+        }
+}
+
+// out[e] = (own[e] + recv_0[e] + ... + recv_{K-1}[e]) mod p   (the local half of a reduce-scatter)
+__global__ void k_sum_pieces(u32 *__restrict__ out, const u32 *__restrict__ own, const u32 *__restrict__ recv, int K,
+                             size_t stride, int64_t count, ModP m)
+{
+        for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x) {
+                u64 acc = own[e];
+                for (int q = 0; q < K; q++) acc += recv[(size_t)q * stride + e];
+                out[e] = mp_reduce(acc, m);
+        }
 }
 
 // y[e] = (z_0[e] + ... + z_{K-1}[e]) mod p
@@ -695,9 +753,12 @@ int mg_prepare(blk_ctx *c, const u32 *p_full_dev)
         return 0;
 }
 
+int grid_iteration(blk_ctx *c, EventTimer *tm);
+
 // one iteration of the loop body, sequential/lanczos_modp.c:635-656
 int enqueue_iteration(blk_ctx *c, EventTimer *tm)
 {
+        if (c->grid_on) return grid_iteration(c, tm);
         if (c->mg_recur) return c->colblocks ? enqueue_iteration_mg_arrival(c, tm) : enqueue_iteration_mg(c, tm);
         const Geometry &g = c->geo;
         const int np = g.np;
@@ -825,6 +886,231 @@ int download_rows(blk_ctx *c, u32 *dst_host, const u32 *src, int64_t rows, const
         return 0;
 }
 
+// ---- P x Q block grid ---------------------------------------------------------------------------
+// The iteration on the grid is specified, and pinned against the oracle, by tests/test_grid_cpu.py; this is
+// its device side.  Not yet run on GPUs (no multi-GPU time was left in round 1): BLK_GRID=PxQ|auto.
+
+// Plan (same rules as blk_plan_grid), block extraction, operators, buffers, sub-communicators.
+// cntN / cntM: entries per row of the N / Mc dimension (host); iN / iM / val: the COO on the device.
+int grid_create(blk_ctx *c, int P, int Q, int chunk_len, int64_t nnz, const int32_t *iN, const int32_t *iM, const u32 *val,
+                const std::vector<u32> &cntN, const std::vector<u32> &cntM)
+{
+        blk_ctx::Grid &G = c->grid;
+        const int np = c->geo.np, W = c->world;
+        if (!g_nccl.Send || !g_nccl.Recv || !g_nccl.CommSplit) return fail("BLK_GRID needs ncclSend / ncclRecv / ncclCommSplit (NCCL >= 2.18)");
+        if (P == 0 && Q == 0) {
+                Q = 1;
+                for (int q = 1; (int64_t)q * q <= W; q++)
+                        if (W % q == 0) Q = q;
+                P = W / Q;
+        }
+        if (P < 1 || Q < 1 || P * Q != W) return fail("BLK_GRID: P x Q must equal the number of ranks");
+        G.P = P; G.Q = Q; G.a = c->rank / Q; G.b = c->rank % Q;
+        G.n_off = partition_rows(cntN, P);
+        G.m_off = partition_rows(cntM, Q);
+        G.n_sub.assign((size_t)P * (Q + 1), 0);
+        G.m_sub.assign((size_t)Q * (P + 1), 0);
+        for (int a = 0; a < P; a++)
+                for (int b = 0; b <= Q; b++) G.n_sub[(size_t)a * (Q + 1) + b] = G.n_off[a] + (G.n_off[a + 1] - G.n_off[a]) * b / Q;
+        for (int b = 0; b < Q; b++)
+                for (int a = 0; a <= P; a++) G.m_sub[(size_t)b * (P + 1) + a] = G.m_off[b] + (G.m_off[b + 1] - G.m_off[b]) * a / P;
+        auto ceil_div = [](int64_t x, int64_t y) { return (x + y - 1) / y; };
+        G.pieceNmax = G.pieceMmax = 1;
+        for (int a = 0; a < P; a++) G.pieceNmax = std::max(G.pieceNmax, ceil_div(G.n_off[a + 1] - G.n_off[a], Q));
+        for (int b = 0; b < Q; b++) G.pieceMmax = std::max(G.pieceMmax, ceil_div(G.m_off[b + 1] - G.m_off[b], P));
+        G.pieceN = std::max<int64_t>(1, ceil_div(G.n_off[G.a + 1] - G.n_off[G.a], Q));
+        G.pieceM = std::max<int64_t>(1, ceil_div(G.m_off[G.b + 1] - G.m_off[G.b], P));
+        const int64_t rowsN = G.pieceN * Q, rowsM = G.pieceM * P;
+
+        // ---- block (a,b) with piece-padded local indices
+        int64_t *dn = nullptr, *dm = nullptr;
+        unsigned long long *cnt = nullptr, h = 0;
+        CU(cudaMalloc(&dn, sizeof(int64_t) * (Q + 1)));
+        CU(cudaMalloc(&dm, sizeof(int64_t) * (P + 1)));
+        CU(cudaMalloc(&cnt, sizeof(unsigned long long)));
+        CU(cudaMemcpyAsync(dn, &G.n_sub[(size_t)G.a * (Q + 1)], sizeof(int64_t) * (Q + 1), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(dm, &G.m_sub[(size_t)G.b * (P + 1)], sizeof(int64_t) * (P + 1), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
+        if (nnz) k_select_grid<<<nb(nnz), 256, 0, c->stream>>>(nnz, iN, iM, val, Q, dn, G.pieceN, P, dm, G.pieceM, nullptr, nullptr, nullptr, cnt);
+        CU(cudaMemcpyAsync(&h, cnt, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        const size_t cap = h ? (size_t)h : 1;
+        int32_t *ln = nullptr, *lm = nullptr;
+        u32 *lx = nullptr;
+        CU(cudaMalloc(&ln, sizeof(int32_t) * cap));
+        CU(cudaMalloc(&lm, sizeof(int32_t) * cap));
+        CU(cudaMalloc(&lx, sizeof(u32) * cap));
+        CU(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
+        if (nnz) k_select_grid<<<nb(nnz), 256, 0, c->stream>>>(nnz, iN, iM, val, Q, dn, G.pieceN, P, dm, G.pieceM, ln, lm, lx, cnt);
+        CU(cudaStreamSynchronize(c->stream));
+        // S1: partial tmp_b (rows: Mc-block b) <- v_a ; S2: partial Av_a (rows: N-block a) <- tmp_b
+        std::string err = build_operator(&G.S1, c->geo, chunk_len, rowsM, rowsN, 0, (int64_t)h, lm, ln, lx, c->m.p, nullptr, nullptr, 1, c->stream);
+        if (err.empty())
+                err = build_operator(&G.S2, c->geo, chunk_len, rowsN, rowsM, 0, (int64_t)h, ln, lm, lx, c->m.p, nullptr, nullptr, 1, c->stream);
+        cudaFree(ln); cudaFree(lm); cudaFree(lx); cudaFree(dn); cudaFree(dm); cudaFree(cnt);
+        if (!err.empty()) return fail("grid block: " + err);
+
+        // ---- buffers
+        const size_t bN = sizeof(u32) * (size_t)rowsN * np, bM = sizeof(u32) * (size_t)rowsM * np;
+        const size_t brecv = sizeof(u32) * (size_t)std::max<int64_t>(1, std::max((P - 1) * G.pieceM, (Q - 1) * G.pieceN)) * np;
+        const size_t bown = sizeof(u32) * (size_t)G.pieceN * np;
+        CU(cudaMalloc(&G.vblk, bN)); CU(cudaMalloc(&G.tblk, bM)); CU(cudaMalloc(&G.part1, bM)); CU(cudaMalloc(&G.part2, bN));
+        CU(cudaMalloc(&G.recv, brecv));
+        CU(cudaMalloc(&G.Av, bown)); CU(cudaMalloc(&G.p, bown));
+        CU(cudaMemsetAsync(G.vblk, 0, bN, c->stream)); CU(cudaMemsetAsync(G.tblk, 0, bM, c->stream));
+        CU(cudaMemsetAsync(G.part1, 0, bM, c->stream)); CU(cudaMemsetAsync(G.part2, 0, bN, c->stream));
+        CU(cudaMemsetAsync(G.recv, 0, brecv, c->stream));
+        CU(cudaMemsetAsync(G.Av, 0, bown, c->stream)); CU(cudaMemsetAsync(G.p, 0, bown, c->stream));
+        c->block_bytes += 2 * bN + 2 * bM + brecv + 2 * bown;
+        CU(cudaStreamSynchronize(c->stream));
+
+        // ---- communicators of my grid row (ranks a*Q .. a*Q+Q-1, my index b) and column (index a)
+        NC(g_nccl.CommSplit(c->comm, G.a, G.b, &G.row_comm, nullptr));
+        NC(g_nccl.CommSplit(c->comm, P + G.b, G.a, &G.col_comm, nullptr));
+        c->grid_on = true;
+        return 0;
+}
+
+void grid_destroy(blk_ctx *c)
+{
+        blk_ctx::Grid &G = c->grid;
+        if (G.row_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(G.row_comm);
+        if (G.col_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(G.col_comm);
+        free_operator(&G.S1); free_operator(&G.S2);
+        cudaFree(G.vblk); cudaFree(G.tblk); cudaFree(G.part1); cudaFree(G.part2); cudaFree(G.recv); cudaFree(G.Av); cudaFree(G.p);
+}
+
+// all-to-all of the pieces of a partial block inside a group + local sum mod p: out <- my piece of the sum
+int grid_reduce_scatter(blk_ctx *c, ncclComm_t comm, int size, int me, const u32 *part, int64_t piece_rows, u32 *out)
+{
+        blk_ctx::Grid &G = c->grid;
+        const size_t cnt = (size_t)piece_rows * c->geo.np;
+        if (size > 1) {
+                NC(g_nccl.GroupStart());
+                for (int k = 0; k < size; k++) {
+                        if (k == me) continue;
+                        NC(g_nccl.Send(part + (size_t)k * cnt, cnt, ncclUint32, k, comm, c->stream));
+                        NC(g_nccl.Recv(G.recv + (size_t)(k < me ? k : k - 1) * cnt, cnt, ncclUint32, k, comm, c->stream));
+                }
+                NC(g_nccl.GroupEnd());
+        }
+        unsigned blocks = (unsigned)std::min<int64_t>(148 * 8, ((int64_t)cnt + 255) / 256);
+        k_sum_pieces<<<blocks ? blocks : 1, 256, 0, c->stream>>>(out, part + (size_t)me * cnt, G.recv, size - 1, cnt, (int64_t)cnt, c->m);
+        c->launches += 1;
+        return 0;
+}
+
+// one iteration on the grid (steps 1-7 of tests/test_grid_cpu.py)
+int grid_iteration(blk_ctx *c, EventTimer *tm)
+{
+        blk_ctx::Grid &G = c->grid;
+        const Geometry &g = c->geo;
+        const int np = g.np;
+        const size_t cN = (size_t)G.pieceN * np, cM = (size_t)G.pieceM * np;
+        u32 *vown = G.vblk + (size_t)G.b * cN;
+        int k;
+        if (tm) tm->begin(c, BLK_PH_EXCHANGE);
+        if (G.Q > 1) NC(g_nccl.AllGather(vown, G.vblk, cN, ncclUint32, G.row_comm, c->stream));
+        if (tm) tm->end(c, 0);
+        if (tm) tm->begin(c, BLK_PH_SPMV1);
+        k = launch_spmv(G.S1, g, c->m, G.vblk, G.part1, c->state, c->stream);
+        c->launches += k;
+        if (tm) tm->end(c, k);
+        if (tm) tm->begin(c, BLK_PH_EXCHANGE);
+        if (grid_reduce_scatter(c, G.col_comm, G.P, G.a, G.part1, G.pieceM, G.tblk + (size_t)G.a * cM)) return 1;
+        if (G.P > 1) NC(g_nccl.AllGather(G.tblk + (size_t)G.a * cM, G.tblk, cM, ncclUint32, G.col_comm, c->stream));
+        if (tm) tm->end(c, 1);
+        if (tm) tm->begin(c, BLK_PH_SPMV2);
+        k = launch_spmv(G.S2, g, c->m, G.tblk, G.part2, c->state, c->stream);
+        c->launches += k;
+        if (tm) tm->end(c, k);
+        if (tm) tm->begin(c, BLK_PH_EXCHANGE);
+        if (grid_reduce_scatter(c, G.row_comm, G.Q, G.b, G.part2, G.pieceN, G.Av)) return 1;
+        if (tm) tm->end(c, 1);
+        if (tm) tm->begin(c, BLK_PH_DOTS);
+        k = launch_dots(g, c->m, G.pieceN, vown, G.Av, c->sums, dots_num_blocks(G.pieceN, np), c->state, SmallFuse(), c->stream);
+        c->launches += k;
+        if (tm) tm->end(c, k);
+        if (tm) tm->begin(c, BLK_PH_EXCHANGE);
+        NC(g_nccl.AllReduce(c->sums, c->sums, (size_t)2 * np * np, ncclUint64, ncclSum, c->comm, c->stream));
+        if (tm) tm->end(c, 0);
+        if (tm) tm->begin(c, BLK_PH_SMALL);
+        k = launch_small(g, c->m, c->sums, c->mats, c->state, 0, c->stream);
+        c->launches += k;
+        if (tm) tm->end(c, k);
+        if (tm) tm->begin(c, BLK_PH_ORTHO);
+        k = launch_ortho(g, c->m, G.pieceN, vown, G.Av, G.p, vown, G.p, c->mats, c->state, 0, c->stream);
+        c->launches += k;
+        if (tm) tm->end(c, k);
+        G.dirty = true;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(e));
+        return 0;
+}
+
+// blk_set_state has put the full v into c->v (device); p_host may be null.  Fill the grid's blocks.
+int grid_import(blk_ctx *c, const u32 *p_host)
+{
+        blk_ctx::Grid &G = c->grid;
+        const int np = c->geo.np, n = c->geo.n, Q = G.Q, P = G.P;
+        const size_t cN = (size_t)G.pieceN * np;
+        CU(cudaMemsetAsync(G.vblk, 0, sizeof(u32) * cN * Q, c->stream));
+        CU(cudaMemsetAsync(G.tblk, 0, sizeof(u32) * (size_t)G.pieceM * np * P, c->stream));
+        CU(cudaMemsetAsync(G.Av, 0, sizeof(u32) * cN, c->stream));
+        CU(cudaMemsetAsync(G.p, 0, sizeof(u32) * cN, c->stream));
+        for (int b = 0; b < Q; b++) {
+                const int64_t lo = G.n_sub[(size_t)G.a * (Q + 1) + b], hi = G.n_sub[(size_t)G.a * (Q + 1) + b + 1];
+                if (hi > lo)
+                        CU(cudaMemcpyAsync(G.vblk + (size_t)b * cN, c->v + (size_t)lo * np, sizeof(u32) * (size_t)(hi - lo) * np,
+                                           cudaMemcpyDeviceToDevice, c->stream));
+        }
+        if (p_host) {
+                const int64_t lo = G.n_sub[(size_t)G.a * (Q + 1) + G.b], hi = G.n_sub[(size_t)G.a * (Q + 1) + G.b + 1];
+                if (hi > lo && upload_rows(c, G.p, p_host + (size_t)lo * n, hi - lo)) return 1;
+        }
+        G.dirty = false;
+        return 0;
+}
+
+// Copy the distributed state into the 1-D blocks everything outside the loop works on: c->v and c->tmp in
+// full on every rank, c->Av and c->p on this rank's 1-D rows [n0, n1).
+int grid_export(blk_ctx *c)
+{
+        blk_ctx::Grid &G = c->grid;
+        if (!G.dirty) return 0;
+        const int np = c->geo.np, P = G.P, Q = G.Q, W = c->world;
+        u32 *stage = nullptr;
+        const size_t slotN = (size_t)G.pieceNmax * np, slotM = (size_t)G.pieceMmax * np;
+        CU(cudaMalloc(&stage, sizeof(u32) * std::max(slotN, slotM) * W));
+        struct Item { const u32 *src; size_t have; bool alongN; u32 *dst; int64_t dlo, dhi; };   // dst covers global rows [dlo, dhi)
+        const Item items[4] = {
+                {G.vblk + (size_t)G.b * G.pieceN * np, (size_t)G.pieceN * np, true, c->v, 0, c->N},
+                {G.tblk + (size_t)G.a * G.pieceM * np, (size_t)G.pieceM * np, false, c->tmp, 0, c->Mc},
+                {G.Av, (size_t)G.pieceN * np, true, c->Av, c->n0(), c->n1()},
+                {G.p, (size_t)G.pieceN * np, true, c->p, c->n0(), c->n1()},
+        };
+        for (const Item &it : items) {
+                const size_t slot = it.alongN ? slotN : slotM;
+                CU(cudaMemsetAsync(stage + (size_t)c->rank * slot, 0, sizeof(u32) * slot, c->stream));
+                CU(cudaMemcpyAsync(stage + (size_t)c->rank * slot, it.src, sizeof(u32) * it.have, cudaMemcpyDeviceToDevice, c->stream));
+                NC(g_nccl.AllGather(stage + (size_t)c->rank * slot, stage, slot, ncclUint32, c->comm, c->stream));
+                for (int r = 0; r < W; r++) {
+                        const int a = r / Q, b = r % Q;
+                        int64_t lo, hi;
+                        if (it.alongN) { lo = G.n_sub[(size_t)a * (Q + 1) + b]; hi = G.n_sub[(size_t)a * (Q + 1) + b + 1]; }
+                        else { lo = G.m_sub[(size_t)b * (P + 1) + a]; hi = G.m_sub[(size_t)b * (P + 1) + a + 1]; }
+                        const int64_t l2 = std::max(lo, it.dlo), h2 = std::min(hi, it.dhi);
+                        if (h2 > l2)
+                                CU(cudaMemcpyAsync(it.dst + (size_t)(l2 - it.dlo) * np, stage + (size_t)r * slot + (size_t)(l2 - lo) * np,
+                                                   sizeof(u32) * (size_t)(h2 - l2) * np, cudaMemcpyDeviceToDevice, c->stream));
+                }
+        }
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(stage);
+        G.dirty = false;
+        return 0;
+}
+
 void destroy_graph(blk_ctx *c)
 {
         if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
@@ -945,6 +1231,7 @@ int blk_destroy(blk_ctx *c)
         cudaSetDevice(c->device);
         if (c->stream) cudaStreamSynchronize(c->stream);
         destroy_graph(c);
+        grid_destroy(c);
         if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
         free_operator(&c->S1);
         free_operator(&c->S2);
@@ -1009,6 +1296,18 @@ int blk_create(blk_ctx **out, const blk_params *prm)
                 const char *er = getenv("BLK_RECUR"), *ep = getenv("BLK_P2P");
                 if (K >= 2 && K <= 16 && !(world > 1 && ((er && er[0] == '0') || (ep && ep[0] == '1')))) c->colblocks = K;
         }
+        // experimental: BLK_GRID=PxQ or BLK_GRID=auto runs the loop on the P x Q block grid (world > 1 only)
+        bool grid_req = false;
+        int gridP = 0, gridQ = 0;
+        {
+                const char *e = getenv("BLK_GRID");
+                if (e && e[0] && world > 1) {
+                        grid_req = true;
+                        if (sscanf(e, "%dx%d", &gridP, &gridQ) != 2) gridP = gridQ = 0;      // "auto": like MPI_Dims_create
+                        c->colblocks = 0;
+                }
+        }
+        std::vector<u32> grid_cntN, grid_cntM;
         const int np = c->geo.np;
 #define CUX(call)                                                                                  \
         do {                                                                                       \
@@ -1061,6 +1360,7 @@ int blk_create(blk_ctx **out, const blk_params *prm)
                         CUX(cudaStreamSynchronize(c->stream));
                         cudaFree(dc);
                         (pass ? c->m_off : c->n_off) = partition_rows(hc, world);
+                        if (grid_req) (pass ? grid_cntM : grid_cntN) = hc;
                 }
         }
 
@@ -1152,7 +1452,7 @@ int blk_create(blk_ctx **out, const blk_params *prm)
                 if (!err.empty()) { free_coo(); fail(err); blk_destroy(c); return 1; }
         }
         CUX(cudaStreamSynchronize(c->stream));
-        free_coo();
+        if (!grid_req) free_coo();          // the grid mode extracts its block after the communicator exists
 
         // ---- vector blocks and the small working set
         int64_t ln = c->n1() - c->n0();
@@ -1262,7 +1562,7 @@ int blk_create(blk_ctx **out, const blk_params *prm)
                         CUX(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
                 }
                 const char *er = getenv("BLK_RECUR");
-                if (!(er && er[0] == '0')) {
+                if (!(er && er[0] == '0') && !grid_req) {
                         c->mg_recur = true;
                         int64_t lm = c->m1() - c->m0();
                         size_t bav = sizeof(u32) * (size_t)gather_cap(c->n_off) * np;
@@ -1325,6 +1625,11 @@ int blk_create(blk_ctx **out, const blk_params *prm)
                                 }
                         }
                 }
+                if (grid_req) {
+                        int rc = grid_create(c, gridP, gridQ, prm->chunk_len, nnz, idxN, idxM, dx, grid_cntN, grid_cntM);
+                        free_coo();
+                        if (rc) { blk_destroy(c); return 1; }
+                }
         }
 #undef CUX
         *out = c;
@@ -1358,6 +1663,7 @@ int blk_set_state(blk_ctx *c, const uint32_t *v, const uint32_t *p, int32_t n_it
                 cudaFree(pfull);
                 if (rc) return 1;
         }
+        if (c->grid_on && grid_import(c, p)) return 1;
         c->ran_since_set = false;
         c->iters = n_iterations; c->stopped = 0;
         c->tmp_is_spmv = false; c->any_ortho = n_iterations > 0;
@@ -1425,6 +1731,7 @@ int blk_get_state(blk_ctx *c, uint32_t *v, uint32_t *tmp, uint32_t *Av, uint32_t
         const int n = c->geo.n, np = c->geo.np;
         const int64_t pad = blk_block_pad(c->nrows, c->ncols, n, c->right);
         const int64_t N = c->N, Mc = c->Mc;
+        if (c->grid_on && grid_export(c)) return 1;
         // v is complete on every rank only right after an all-gather; refresh it
         if (c->world > 1 && allgather_rows(c, c->v, c->n_off)) return 1;
         std::vector<u32> hv;
@@ -1499,6 +1806,7 @@ int blk_final_check(blk_ctx *c, int32_t *v_nonzero, int32_t *vtm_zero)
         CU(cudaSetDevice(c->device));
         const int np = c->geo.np;
         int nz = 0, big = 0;
+        if (c->grid_on && grid_export(c)) return 1;
         // v: every rank scans its own rows (padding columns are zero)
         if (scan_rows(c, c->v + (size_t)c->n0() * np, c->n1() - c->n0(), &nz, &big)) return 1;
         *v_nonzero = nz;
