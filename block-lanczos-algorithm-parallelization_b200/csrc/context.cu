@@ -887,7 +887,7 @@ int download_rows(blk_ctx *c, u32 *dst_host, const u32 *src, int64_t rows, const
 }
 
 // ---- P x Q block grid ---------------------------------------------------------------------------
-// The iteration on the grid is specified, and pinned against the oracle, by tests/test_grid_cpu.py; this is
+// The iteration on the grid is specified, and pinned bit for bit on the CPU, by tests/test_grid_cpu.py; this is
 // its device side.  Not yet run on GPUs (no multi-GPU time was left in round 1): BLK_GRID=PxQ|auto.
 
 // Plan (same rules as blk_plan_grid), block extraction, operators, buffers, sub-communicators.
