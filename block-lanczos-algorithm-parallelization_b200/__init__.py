@@ -22,12 +22,13 @@ LIB_PATH = os.path.join(PKG_DIR, "libblklanczos.so")
 BLK_ABI_VERSION = 1
 BLK_MAX_N = 64
 BLK_NCCL_ID_BYTES = 128
+BLK_RANK_ALL = -1          # blk_params.rank: one context (one process) drives all `world` GPUs
 PHASES = ("spmv1", "spmv2", "dots", "small", "ortho", "exchange")
 
 # every symbol include/blk_lanczos.h declares
 ABI_SYMBOLS = (
     "blk_abi_version", "blk_last_error", "blk_device_count", "blk_nccl_unique_id", "blk_create",
-    "blk_destroy", "blk_plan_shards", "blk_plan_grid", "blk_block_pad", "blk_set_state", "blk_iterate", "blk_get_state", "blk_final_check",
+    "blk_destroy", "blk_plan_shards", "blk_plan_grid", "blk_block_pad", "blk_set_state", "blk_iterate", "blk_get_state", "blk_get_state_local", "blk_final_check",
     "blk_check_kernel_block", "blk_get_small",
     "blk_spmv", "blk_block_dot_products", "blk_semi_inverse", "blk_orthogonalize",
     "blk_set_profiling", "blk_get_phase_times", "blk_time_spmv", "blk_kernel_launches", "blk_get_info",
@@ -84,6 +85,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.blk_set_state.argtypes = [vp, vp, vp, i32]
     L.blk_iterate.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
     L.blk_get_state.argtypes = [vp, vp, vp, vp, vp]
+    L.blk_get_state_local.argtypes = [vp, vp, vp, vp]
     L.blk_final_check.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
     L.blk_check_kernel_block.argtypes = [vp, vp, C.POINTER(i32)]
     L.blk_get_small.argtypes = [vp, vp, vp, vp, vp, C.POINTER(i32)]
@@ -169,7 +171,8 @@ class BlockLanczos:
                  rank: int = 0, world: int = 1, nccl_id: bytes | None = None, stream: int | None = None,
                  chunk_len: int = 0, use_graph: int = -1, device_coo=None):
         """`M` is a host SparseCOO; alternatively `device_coo=(nrows, ncols, nnz, i_ptr, j_ptr, x_ptr)`
-        gives raw CUDA device pointers (int32, int32, uint32) on `device`."""
+        gives raw CUDA device pointers (int32, int32, uint32) on `device`.  `rank=BLK_RANK_ALL` with
+        `world=W` makes ONE context drive W GPUs (devices device..device+W-1) from this process."""
         self.L = load_library()
         self.n, self.prime, self.right = int(n), int(prime), bool(right)
         prm = blk_params()
@@ -283,6 +286,10 @@ class BlockLanczos:
         self._ck(self.L.blk_get_state(self.h, _ptr(out.get("v")), _ptr(out.get("tmp")),
                                       _ptr(out.get("Av")), _ptr(out.get("p"))))
         return out
+
+    def get_state_local(self, v=None, Av=None, p_blk=None):
+        """Multi-process jobs: write only this rank's rows of v / Av / p into the given padded blocks."""
+        self._ck(self.L.blk_get_state_local(self.h, _ptr(v), _ptr(Av), _ptr(p_blk)))
 
     def final_check(self):
         """(v != 0, M^T v == 0) evaluated on the device; sequential/lanczos_modp.c:560-582."""

@@ -5,6 +5,7 @@ snapshot.  nvcc cross-compiles without a GPU.
 """
 from __future__ import annotations
 
+import glob
 import os
 import subprocess
 import sys
@@ -31,8 +32,8 @@ def _stale(target: str, sources: list[str]) -> bool:
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
     srcs = [os.path.join(CSRC, s) for s in CU_SOURCES]
-    deps = srcs + [os.path.join(CSRC, h) for h in ("modp.cuh", "blk_internal.cuh")] + \
-        [os.path.join(ROOT, "include", "blk_lanczos.h")]
+    # every header any translation unit can include: editing one of them must rebuild the library
+    deps = srcs + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + sorted(glob.glob(os.path.join(ROOT, "include", "*.h")))
     if not force and not _stale(LIB, deps):
         return LIB
     objs = []

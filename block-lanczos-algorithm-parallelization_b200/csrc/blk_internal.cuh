@@ -55,7 +55,9 @@ struct DevSmall {
         int do_ortho;     // set by the small kernel of the current iteration
         int npiv;         // last semi_inverse return value
         int bad_index;    // layout build: COO index out of range
-        int pad_;
+        int check;        // BLK_CHECK=1: evaluate the reference's correctness_tests in the n x n stage
+        int check_failed; // bit mask of the violated invariants (the loop halts; blk_iterate reports it)
+        int fault_iter;   // BLK_CHECK_FAULT=k (with BLK_CHECK=1): corrupt vtAv in iteration k, to test the self-check
 };
 
 struct Geometry {
@@ -76,6 +78,20 @@ static inline Geometry make_geometry(int n)
         return g;
 }
 
+// number of SMs of the current device (cached per ordinal): grids are sized in multiples of it
+static inline int blk_sm_count()
+{
+        static int cache[64] = {0};
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+        if (!cache[dev]) {
+                int n = 0;
+                if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+                cache[dev] = n;
+        }
+        return cache[dev];
+}
+
 // ---- launchers (each returns the number of kernels it launched) ---------------------------
 // layout_build.cu
 std::string build_operator(SpOp *op, const Geometry &geo, int chunk_len, int64_t rows, int64_t cols,
@@ -87,10 +103,20 @@ void free_operator(SpOp *op);
 std::string degree_sort_maps(int64_t nnz, const int32_t *d_idx, int64_t dim, u32 **old2new, u32 **new2old,
                              cudaStream_t st);
 
+// Peer copies of an output block (multi-GPU, peer-mapped device pointers): y[q] addresses the same
+// row origin on peer q as the local output pointer of the launch, so a finished row r goes to
+// y[q] + r*n_pad on every peer.
+struct PushTargets {
+        static constexpr int MAX = 7;
+        int n = 0;
+        u32 *y[MAX] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
 // spmv.cu
-// piece < 0: the whole operator; else only tiles (and the fix-up) of that row piece
+// piece < 0: the whole operator; else only tiles (and the fix-up) of that row piece.
+// push (nullable): also store every finished row into the peers' copies (fused all-gather).
 int launch_spmv(const SpOp &op, const Geometry &geo, const ModP &m, const u32 *x, u32 *y,
-                const DevSmall *state, cudaStream_t st, int piece = -1);
+                const DevSmall *state, cudaStream_t st, int piece = -1, const PushTargets *push = nullptr);
 
 // dense.cu
 int dots_num_blocks(int64_t rows, int np);
@@ -139,7 +165,8 @@ int launch_ortho_umma(int np, const ModP &m, int64_t rows, u32 *v, const u32 *Av
                       const u32 *mats, const DevSmall *state, int force, cudaStream_t st, int variant = -1);
 // per-device one-time kernel attributes (call with the device current, outside stream capture)
 void dense_prepare(const Geometry &geo, const ModP &m);
-// n <-> n_pad repacking of row-major blocks (rows x n  <->  rows x np)
-// `map` (nullable) relabels rows: pad: dst[r] = src[map[r]]; unpad: dst[r] = src[map[r]]
-int launch_pad_rows(const u32 *src, u32 *dst, int64_t rows, int n, int np, const u32 *map, cudaStream_t st);
-int launch_unpad_rows(const u32 *src, u32 *dst, int64_t rows, int n, int np, const u32 *map, cudaStream_t st);
+// n <-> n_pad repacking of row-major blocks (rows x n  <->  rows x np), `rows` rows starting at host row r0.
+// `map` (nullable, old label -> new label) relabels rows: pad scatters src row r to dst row map[r0 + r],
+// unpad gathers dst row r from src row map[r0 + r]; without a map row r <-> row r of the given pointers.
+int launch_pad_rows(const u32 *src, u32 *dst, int64_t rows, int n, int np, const u32 *map, int64_t r0, cudaStream_t st);
+int launch_unpad_rows(const u32 *src, u32 *dst, int64_t rows, int n, int np, const u32 *map, int64_t r0, cudaStream_t st);

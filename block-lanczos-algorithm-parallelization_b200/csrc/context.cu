@@ -15,10 +15,12 @@
 // hand-rolled Send/Recv reductions on a root (mpi/lanczos_modp.c:1088-1125, 1209-1256).
 #include <dlfcn.h>
 #include <nccl.h>
+#include <unistd.h>
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 #include "../../include/blk_lanczos.h"
 #include "blk_internal.cuh"
@@ -129,11 +131,19 @@ struct blk_ctx {
         u32 *Av_full = nullptr;                  // gather target of Av; c->Av points at the local rows inside it
         u32 *Tp = nullptr, *U = nullptr;         // local rows of S1*p and of S1*Av
         u32 *tmp_prev = nullptr;                 // local rows of the previous tmp (only when Mc > N, for checkpoints)
-        // one-sided exchange: finished pieces are pushed into the peers' buffers by the copy engines
-        // (cudaMemcpyAsync on IPC-mapped peer pointers) -- no SMs taken from the sparse product, unlike
-        // NCCL's broadcast kernels; a (tiny) all-reduce that follows is the barrier
-        bool p2p = false;
-        std::vector<u32 *> peer_tmp, peer_av;    // [world] IPC mappings of every rank's tmp / Av_full (own = local)
+        // How the two full-length vectors of an iteration (Av, new tmp) reach the other GPUs:
+        //   XCH_NCCL  grouped ncclBroadcast of every finished row piece on comm_stream (round-1 default)
+        //   XCH_CE    the copy engines push finished pieces into the peers' buffers (cudaMemcpyAsync on peer pointers)
+        //   XCH_PUSH  stores over NVLink from our own kernels through peer-mapped pointers: product 2 writes every
+        //             finished row of Av into all copies itself (k_spmv PUSH, a fused all-gather), the pieces of the new
+        //             tmp are pushed by k_push_rows, a copy kernel of a few CTAs on comm_stream; a tiny all-reduce
+        //             that follows is the barrier
+        enum { XCH_NCCL = 0, XCH_CE = 1, XCH_PUSH = 2 };
+        int xch = XCH_NCCL;
+        bool push_av_in_spmv = true;             // XCH_PUSH: Av from inside k_spmv (else k_push_rows per piece)
+        int push_ctas = 32;
+        std::vector<u32 *> peer_tmp, peer_av;    // [world] peer mappings of every rank's tmp / Av_full (own = local)
+        std::vector<char> peer_ipc;              // [world] mapping came from cudaIpcOpenMemHandle (must be closed)
         std::vector<cudaStream_t> copy_streams;  // one per peer offset so that the copies use several copy engines
         std::vector<cudaEvent_t> ev_copies;
         u64 *barrier_word = nullptr;
@@ -170,6 +180,17 @@ struct blk_ctx {
                 bool dirty = false;                                  // the 1-D copies are stale
         } grid;
         bool grid_on = false;
+        // resident staging buffer of upload_rows / download_rows (host <-> device repacking, chunk by chunk)
+        static constexpr size_t STAGE_BYTES = 32u << 20;
+        u32 *stage = nullptr;
+        long long l2_persist_before = -1;       // cudaLimitPersistingL2CacheSize found at create time (restored on destroy)
+        bool check = false;                     // BLK_CHECK=1: the n x n stage asserts the reference's correctness_tests
+        int check_fault = 0;                    // BLK_CHECK_FAULT=k: corrupt vtAv in iteration k (tests the self-check)
+        // Single-process multi-GPU job (blk_params.rank == BLK_RANK_ALL): this context owns one member context
+        // per GPU and fans every call out to them, one host thread per member (the reference's MPI build is one
+        // process per rank, mpi/lanczos_modp.c:1829-1863; here one process can drive the whole box).
+        std::vector<blk_ctx *> members;
+        bool is_group() const { return !members.empty(); }
         // loop bookkeeping
         int iters = 0, stopped = 0;
         bool tmp_is_spmv = false;               // tmp rows [0,Mc) hold S1*v of the current v (stop case)
@@ -192,6 +213,26 @@ struct blk_ctx {
 };
 
 namespace {
+
+// run f(member, rank) for every member of a group context, one host thread per member (collectives inside the
+// library need all ranks in flight at once); the first failure becomes the group's error
+template <class F> int group_run(blk_ctx *g, F f)
+{
+        const int W = (int)g->members.size();
+        std::vector<int> rc((size_t)W, 0);
+        std::vector<std::string> why((size_t)W);
+        std::vector<std::thread> th;
+        auto body = [&](int r) {
+                rc[(size_t)r] = f(g->members[(size_t)r], r);
+                if (rc[(size_t)r]) why[(size_t)r] = g_err;
+        };
+        for (int r = 1; r < W; r++) th.emplace_back(body, r);
+        body(0);
+        for (auto &t : th) t.join();
+        for (int r = 0; r < W; r++)
+                if (rc[(size_t)r]) return fail("GPU " + std::to_string(g->members[(size_t)r]->device) + ": " + why[(size_t)r]);
+        return 0;
+}
 
 struct EventTimer {
         // records (phase, start, stop) triples on the stream; resolved after a sync
@@ -394,7 +435,7 @@ int scan_rows(blk_ctx *c, const u32 *a, int64_t rows, int *any_nonzero, int *any
         CU(cudaMemsetAsync(flags, 0, 2 * sizeof(int), c->stream));
         int64_t count = rows * c->geo.np;
         if (count > 0) {
-                unsigned blocks = (unsigned)std::min<int64_t>(148 * 8, (count + 255) / 256);
+                unsigned blocks = (unsigned)std::min<int64_t>(blk_sm_count() * 8, (count + 255) / 256);
                 k_scan_block<<<blocks, 256, 0, c->stream>>>(a, count, c->m.p, flags);
                 c->launches++;
         }
@@ -554,7 +595,7 @@ int colblock_product(blk_ctx *c, blk_ctx::ColOps &ops, const u32 *x, u32 *y, con
                 if (hi > lo) {
                         k += launch_spmv(ops.last[i], c->geo, c->m, x, c->zbuf + (size_t)(K - 1) * c->zstride + (size_t)lo * np, state, c->stream);
                         const int64_t cnt = (hi - lo) * np;
-                        unsigned blocks = (unsigned)std::min<int64_t>(148 * 8, (cnt + 255) / 256);
+                        unsigned blocks = (unsigned)std::min<int64_t>(blk_sm_count() * 8, (cnt + 255) / 256);
                         k_combine_blocks<<<blocks, 256, 0, c->stream>>>(y + (size_t)lo * np, c->zbuf + (size_t)lo * np, K, c->zstride, cnt, c->m, state);
                         k += 1;
                 }
@@ -563,13 +604,89 @@ int colblock_product(blk_ctx *c, blk_ctx::ColOps &ops, const u32 *x, u32 *y, con
         return k;
 }
 
+// Copy rows [first16, first16 + count16) (in 16-byte units) of a block into the same place of every peer's copy:
+// the exchange of a finished row piece over NVLink with plain coalesced stores.  A few CTAs saturate the
+// link; running on the high-priority side stream they slip in between the blocks of the sparse product.
+__global__ void __launch_bounds__(512)
+k_push_rows(const uint4 *__restrict__ src, PushTargets push, size_t first16, size_t count16, const DevSmall *__restrict__ state)
+{
+        if (state && !state->do_ortho) return;            // the piece was not rewritten (halted iteration)
+        const uint4 *s4 = src + first16;
+        const size_t stride = (size_t)gridDim.x * blockDim.x;
+        size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; i + 3 * stride < count16; i += 4 * stride) {
+                uint4 a = __ldcg(s4 + i), b = __ldcg(s4 + i + stride), c = __ldcg(s4 + i + 2 * stride), d = __ldcg(s4 + i + 3 * stride);
+                for (int q = 0; q < push.n; q++) {
+                        uint4 *dst = reinterpret_cast<uint4 *>(push.y[q]) + first16;
+                        dst[i] = a; dst[i + stride] = b; dst[i + 2 * stride] = c; dst[i + 3 * stride] = d;
+                }
+        }
+        for (; i < count16; i += stride) {
+                uint4 a = __ldcg(s4 + i);
+                for (int q = 0; q < push.n; q++) (reinterpret_cast<uint4 *>(push.y[q]) + first16)[i] = a;
+        }
+}
+
+// peers' copies of a block, addressed from row `row0` on (see PushTargets)
+PushTargets push_targets(const blk_ctx *c, const std::vector<u32 *> &peers, int64_t row0)
+{
+        PushTargets t;
+        for (int s = 1; s < c->world && t.n < PushTargets::MAX; s++) {
+                const int d = (c->rank + s) % c->world;             // staggered: rank r starts with peer r+1
+                t.y[t.n++] = peers[d] + (size_t)row0 * c->geo.np;
+        }
+        return t;
+}
+
+// piece q of my rows of a row-sharded block -> every peer (one of the three exchange modes); `ready` fires when the
+// piece is final.  state != null: the piece may be unchanged (k_push_rows then returns at once).
+int exchange_piece(blk_ctx *c, u32 *buf, const std::vector<u32 *> &peers, const std::vector<int64_t> &off,
+                   const std::vector<int64_t> &rows_all, int K, int q, cudaEvent_t ready, const DevSmall *state)
+{
+        if (c->xch == blk_ctx::XCH_CE) return piece_push(c, peers, off, rows_all, K, q, ready);
+        CU(cudaStreamWaitEvent(c->comm_stream, ready, 0));
+        if (c->xch == blk_ctx::XCH_NCCL) return piece_broadcast(c, buf, off, rows_all, K, q, c->comm_stream);
+        const int64_t lo = rows_all[(size_t)c->rank * (K + 1) + q], hi = rows_all[(size_t)c->rank * (K + 1) + q + 1];
+        const size_t per_row = (size_t)c->geo.np * sizeof(u32);
+        // blocks start on 16-byte boundaries: row counts times np*4 bytes with np*4 a multiple of 16 for np >= 4;
+        // for np < 4 the piece boundaries are rounded by the caller of this mode (see blk_create)
+        const size_t first = (size_t)(off[c->rank] + lo) * per_row, bytes = (size_t)(hi - lo) * per_row;
+        if (bytes == 0) return 0;
+        if ((first | bytes) & 15) return fail("push exchange: piece not 16-byte aligned");
+        PushTargets t = push_targets(c, peers, 0);
+        const size_t count16 = bytes / 16;
+        unsigned blocks = (unsigned)std::min<size_t>((size_t)c->push_ctas, (count16 + 511) / 512);
+        k_push_rows<<<blocks, 512, 0, c->comm_stream>>>(reinterpret_cast<const uint4 *>(buf), t, first / 16, count16, state);
+        c->launches++;
+        return 0;
+}
+
+// everything this rank has sent in the current exchange has left, and -- after the all-reduce that every rank
+// enters only then -- everything sent to this rank has landed
+int exchange_done(blk_ctx *c, bool have_allreduce_next)
+{
+        if (c->xch == blk_ctx::XCH_CE) {
+                if (pushes_done(c)) return 1;
+                if (!have_allreduce_next)
+                        NC(g_nccl.AllReduce(c->barrier_word, c->barrier_word, 1, ncclUint64, ncclSum, c->comm, c->stream));
+                return 0;
+        }
+        if (c->xch == blk_ctx::XCH_PUSH && !have_allreduce_next)
+                NC(g_nccl.AllReduce(c->barrier_word, c->barrier_word, 1, ncclUint64, ncclSum, c->comm, c->comm_stream));
+        CU(cudaEventRecord(c->ev_comm, c->comm_stream));
+        CU(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
+        return 0;
+}
+
 // Multi-GPU iteration.  Invariant at entry: tmp (full length, on every rank) = S1 v for the current
 // v, Tp (local rows) = S1 p.  Because S1 is linear and the n x n factors act on the right,
 //     S1 v' = sel(d, S1 Av, S1 v) + (S1 v) c + (S1 p) vtAvd,      S1 p' = sel(d, 0, S1 p) + (S1 v) winv
 // i.e. exactly orthogonalize() applied to (tmp, S1 Av, Tp).  All values are canonical residues, so
 // this is bit-identical to recomputing S1 v'.  What it buys: the only full-length vectors that
-// cross NVLink are Av and the new tmp, and both are produced by a sparse product that runs in
-// row pieces, so each piece travels while the next is computed; the new v is never gathered.
+// cross NVLink are Av and the new tmp.  Av leaves from inside the product that computes it (XCH_PUSH:
+// k_spmv stores every finished row into all copies, nothing is left to wait for but a barrier); the new tmp is
+// produced in row pieces (product piece -> row-wise update -> exchange of the piece while the next one is
+// computed); the new v is never gathered.
 int enqueue_iteration_mg(blk_ctx *c, EventTimer *tm)
 {
         const Geometry &g = c->geo;
@@ -578,17 +695,19 @@ int enqueue_iteration_mg(blk_ctx *c, EventTimer *tm)
         const int64_t lrows = c->n1() - c->n0();
         u32 *vloc = c->v + (size_t)c->n0() * np;
         u32 *tloc = c->tmp + (size_t)c->m0() * np;
+        const bool fused_av = c->xch == blk_ctx::XCH_PUSH && c->push_av_in_spmv;
 
-        // Av <- S2 tmp, piece by piece; every finished piece is broadcast while the next one runs
+        // Av <- S2 tmp
         if (tm) tm->begin(c, BLK_PH_SPMV2);
-        for (int q = 0; q < c->pieces2; q++) {
-                k += launch_spmv(c->S2, g, c->m, c->tmp, c->Av, c->state, c->stream, q);
-                CU(cudaEventRecord(c->ev_piece[q], c->stream));
-                if (c->p2p) {
-                        if (piece_push(c, c->peer_av, c->n_off, c->piece_rows_all2, c->pieces2, q, c->ev_piece[q])) return 1;
-                } else {
-                        CU(cudaStreamWaitEvent(c->comm_stream, c->ev_piece[q], 0));
-                        if (piece_broadcast(c, c->Av_full, c->n_off, c->piece_rows_all2, c->pieces2, q, c->comm_stream)) return 1;
+        if (fused_av) {
+                PushTargets t = push_targets(c, c->peer_av, c->n0());
+                k += launch_spmv(c->S2, g, c->m, c->tmp, c->Av, c->state, c->stream, -1, &t);
+        } else {
+                // piece by piece; every finished piece travels while the next one runs
+                for (int q = 0; q < c->pieces2; q++) {
+                        k += launch_spmv(c->S2, g, c->m, c->tmp, c->Av, c->state, c->stream, q);
+                        CU(cudaEventRecord(c->ev_piece[q], c->stream));
+                        if (exchange_piece(c, c->Av_full, c->peer_av, c->n_off, c->piece_rows_all2, c->pieces2, q, c->ev_piece[q], nullptr)) return 1;
                 }
         }
         c->launches += k;
@@ -600,14 +719,9 @@ int enqueue_iteration_mg(blk_ctx *c, EventTimer *tm)
         c->launches += k;
         if (tm) tm->end(c, k);
         if (tm) tm->begin(c, BLK_PH_EXCHANGE);
-        if (c->p2p) {
-                // my pushes are done when the copy stream drains; the all-reduce below completes only
-                // after every rank has reached it, i.e. after every rank's pushes have landed
-                if (pushes_done(c)) return 1;
-        } else {
-                CU(cudaEventRecord(c->ev_comm, c->comm_stream));
-                CU(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
-        }
+        // the all-reduce below completes only after every rank has reached it, i.e. (stream order) after every
+        // rank's product 2 and its pushes: it is the barrier of the Av exchange
+        if (!fused_av && exchange_done(c, true)) return 1;
         NC(g_nccl.AllReduce(c->sums, c->sums, (size_t)2 * np * np, ncclUint64, ncclSum, c->comm, c->stream));
         if (tm) tm->end(c, 0);
         if (tm) tm->begin(c, BLK_PH_SMALL);
@@ -621,7 +735,7 @@ int enqueue_iteration_mg(blk_ctx *c, EventTimer *tm)
 
         // tmp <- S1 v' through the recurrence: U = S1 Av (never skipped: the limit may just have been
         // reached), then orthogonalize(tmp, U, Tp) on the finished rows (skipped exactly when the real
-        // orthogonalize is), then broadcast
+        // orthogonalize is), then the exchange of the piece
         if (c->tmp_prev)
                 CU(cudaMemcpyAsync(c->tmp_prev, tloc, sizeof(u32) * (size_t)(c->m1() - c->m0()) * np,
                                    cudaMemcpyDeviceToDevice, c->stream));
@@ -634,23 +748,12 @@ int enqueue_iteration_mg(blk_ctx *c, EventTimer *tm)
                         k += launch_ortho(g, c->m, hi - lo, tloc + (size_t)lo * np, c->U + (size_t)lo * np, c->Tp + (size_t)lo * np,
                                           tloc + (size_t)lo * np, c->Tp + (size_t)lo * np, c->mats, c->state, 0, c->stream);
                 CU(cudaEventRecord(c->ev_piece[q], c->stream));
-                if (c->p2p) {
-                        if (piece_push(c, c->peer_tmp, c->m_off, c->piece_rows_all, c->pieces, q, c->ev_piece[q])) return 1;
-                } else {
-                        CU(cudaStreamWaitEvent(c->comm_stream, c->ev_piece[q], 0));
-                        if (piece_broadcast(c, c->tmp, c->m_off, c->piece_rows_all, c->pieces, q, c->comm_stream)) return 1;
-                }
+                if (exchange_piece(c, c->tmp, c->peer_tmp, c->m_off, c->piece_rows_all, c->pieces, q, c->ev_piece[q], c->state)) return 1;
         }
         c->launches += k;
         if (tm) tm->end(c, k);
         if (tm) tm->begin(c, BLK_PH_EXCHANGE);
-        if (c->p2p) {
-                if (pushes_done(c)) return 1;
-                NC(g_nccl.AllReduce(c->barrier_word, c->barrier_word, 1, ncclUint64, ncclSum, c->comm, c->stream));   // barrier
-        } else {
-                CU(cudaEventRecord(c->ev_comm, c->comm_stream));
-                CU(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
-        }
+        if (exchange_done(c, false)) return 1;
         if (tm) tm->end(c, 0);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(e));
@@ -848,9 +951,11 @@ int pull_state(blk_ctx *c)
         return 0;
 }
 
-// host block (rows x n, row-major) -> device block with leading dimension np
-// `map` (device, nullable): dst row r comes from host row map[r]
-int upload_rows(blk_ctx *c, u32 *dst, const u32 *src_host, int64_t rows, const u32 *map = nullptr)
+// host block (rows x n, row-major) -> device block with leading dimension np.  `map` (device, nullable: old
+// label -> new label, whole dimension): host row r0 + r goes to device row map[r0 + r] of `dst`; without a map to
+// row r of `dst`.  Repacking goes through a resident 64 MB staging buffer, chunk by chunk in stream order (the
+// PCIe copy dominates; no allocation per call).
+int upload_rows(blk_ctx *c, u32 *dst, const u32 *src_host, int64_t rows, const u32 *map = nullptr, int64_t r0 = 0)
 {
         const int n = c->geo.n, np = c->geo.np;
         if (rows == 0) return 0;
@@ -859,16 +964,17 @@ int upload_rows(blk_ctx *c, u32 *dst, const u32 *src_host, int64_t rows, const u
                 CU(cudaStreamSynchronize(c->stream));
                 return 0;
         }
-        u32 *stage = nullptr;
-        CU(cudaMalloc(&stage, sizeof(u32) * (size_t)rows * n));
-        CU(cudaMemcpyAsync(stage, src_host, sizeof(u32) * (size_t)rows * n, cudaMemcpyHostToDevice, c->stream));
-        c->launches += launch_pad_rows(stage, dst, rows, n, np, map, c->stream);
+        const int64_t per = std::max<int64_t>(1, (int64_t)(2 * blk_ctx::STAGE_BYTES / (sizeof(u32) * n)));
+        for (int64_t at = 0; at < rows; at += per) {
+                const int64_t cnt = std::min(per, rows - at);
+                CU(cudaMemcpyAsync(c->stage, src_host + (size_t)at * n, sizeof(u32) * (size_t)cnt * n, cudaMemcpyHostToDevice, c->stream));
+                c->launches += launch_pad_rows(c->stage, map ? dst : dst + (size_t)at * np, cnt, n, np, map, r0 + at, c->stream);
+        }
         CU(cudaStreamSynchronize(c->stream));
-        cudaFree(stage);
         return 0;
 }
-// `map` (device, nullable): host row r comes from device row map[r]
-int download_rows(blk_ctx *c, u32 *dst_host, const u32 *src, int64_t rows, const u32 *map = nullptr)
+// `map` (device, nullable): host row r0 + r comes from device row map[r0 + r] of `src` (else row r of `src`)
+int download_rows(blk_ctx *c, u32 *dst_host, const u32 *src, int64_t rows, const u32 *map = nullptr, int64_t r0 = 0)
 {
         const int n = c->geo.n, np = c->geo.np;
         if (rows == 0) return 0;
@@ -877,12 +983,13 @@ int download_rows(blk_ctx *c, u32 *dst_host, const u32 *src, int64_t rows, const
                 CU(cudaStreamSynchronize(c->stream));
                 return 0;
         }
-        u32 *stage = nullptr;
-        CU(cudaMalloc(&stage, sizeof(u32) * (size_t)rows * n));
-        c->launches += launch_unpad_rows(src, stage, rows, n, np, map, c->stream);
-        CU(cudaMemcpyAsync(dst_host, stage, sizeof(u32) * (size_t)rows * n, cudaMemcpyDeviceToHost, c->stream));
+        const int64_t per = std::max<int64_t>(1, (int64_t)(2 * blk_ctx::STAGE_BYTES / (sizeof(u32) * n)));
+        for (int64_t at = 0; at < rows; at += per) {
+                const int64_t cnt = std::min(per, rows - at);
+                c->launches += launch_unpad_rows(map ? src : src + (size_t)at * np, c->stage, cnt, n, np, map, r0 + at, c->stream);
+                CU(cudaMemcpyAsync(dst_host + (size_t)at * n, c->stage, sizeof(u32) * (size_t)cnt * n, cudaMemcpyDeviceToHost, c->stream));
+        }
         CU(cudaStreamSynchronize(c->stream));
-        cudaFree(stage);
         return 0;
 }
 
@@ -994,7 +1101,7 @@ int grid_reduce_scatter(blk_ctx *c, ncclComm_t comm, int size, int me, const u32
                 }
                 NC(g_nccl.GroupEnd());
         }
-        unsigned blocks = (unsigned)std::min<int64_t>(148 * 8, ((int64_t)cnt + 255) / 256);
+        unsigned blocks = (unsigned)std::min<int64_t>(blk_sm_count() * 8, ((int64_t)cnt + 255) / 256);
         k_sum_pieces<<<blocks ? blocks : 1, 256, 0, c->stream>>>(out, part + (size_t)me * cnt, G.recv, size - 1, cnt, (int64_t)cnt, c->m);
         c->launches += 1;
         return 0;
@@ -1137,6 +1244,544 @@ int kernels_per_iteration(const blk_ctx *c) { return c->fuse_small ? 6 : 7; }
 
 }  // namespace
 
+// ---- blk_create, in pieces ------------------------------------------------------------------------
+namespace {
+
+// device allocations that live only during blk_create: freed on every exit path
+struct Scratch {
+        std::vector<void *> ptrs;
+        ~Scratch() { for (void *q : ptrs) cudaFree(q); }
+        template <class T> int alloc(T **out, size_t bytes)
+        {
+                *out = nullptr;
+                cudaError_t e = cudaMalloc((void **)out, bytes ? bytes : 16);
+                if (e != cudaSuccess) return fail(std::string("cudaMalloc (blk_create scratch): ") + cudaGetErrorString(e));
+                ptrs.push_back(*out);
+                return 0;
+        }
+        void release(void *q)
+        {
+                for (auto &x : ptrs)
+                        if (x == q) { cudaFree(q); x = nullptr; }
+        }
+};
+
+bool env_flag(const char *name)
+{
+        const char *e = getenv(name);
+        return e && e[0] && e[0] != '0';
+}
+
+// entries per row of one dimension (host copy)
+int count_dimension(blk_ctx *c, int64_t nnz, const int32_t *idx, int64_t dim, std::vector<u32> *out)
+{
+        Scratch tmp;
+        u32 *dc = nullptr;
+        if (tmp.alloc(&dc, sizeof(u32) * (size_t)dim)) return 1;
+        CU(cudaMemsetAsync(dc, 0, sizeof(u32) * (size_t)dim, c->stream));
+        if (nnz) k_count_rows<<<nb(nnz), 256, 0, c->stream>>>(nnz, idx, dim, dc);
+        out->assign((size_t)dim, 0);
+        if (dim) CU(cudaMemcpyAsync(out->data(), dc, sizeof(u32) * (size_t)dim, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        return 0;
+}
+
+void single_piece(SpOp *op)
+{
+        op->piece_tile.assign({0, op->ntiles});
+        op->piece_row.assign({0, op->rows});
+        op->piece_scan.assign({0, 0});
+}
+
+// Every rank needs every rank's piece boundaries of both operators, and all ranks must use the same number
+// of pieces: build_operator falls back to one piece on a rank whose shard has too few tiles, so the counts
+// are compared here and, on any disagreement, EVERY rank drops to one piece (operator included).
+int agree_pieces(blk_ctx *c)
+{
+        const int world = c->world;
+        for (int which = 0; which < 2; which++) {
+                SpOp &op = which ? c->S2 : c->S1;
+                const int KMAX = 32;
+                std::vector<long long> mine(KMAX + 2, 0), all((size_t)(KMAX + 2) * world, 0);
+                int K = (int)op.piece_tile.size() - 1;
+                mine[0] = K;
+                for (int k = 0; k <= K; k++) mine[1 + k] = op.piece_row[k];
+                Scratch tmp;
+                long long *dbuf = nullptr;
+                if (tmp.alloc(&dbuf, sizeof(long long) * all.size())) return 1;
+                CU(cudaMemcpyAsync(dbuf + (size_t)c->rank * (KMAX + 2), mine.data(), sizeof(long long) * (KMAX + 2),
+                                   cudaMemcpyHostToDevice, c->stream));
+                NC(g_nccl.AllGather(dbuf + (size_t)c->rank * (KMAX + 2), dbuf, (size_t)(KMAX + 2), ncclInt64, c->comm, c->stream));
+                CU(cudaMemcpyAsync(all.data(), dbuf, sizeof(long long) * all.size(), cudaMemcpyDeviceToHost, c->stream));
+                CU(cudaStreamSynchronize(c->stream));
+                bool same = true;
+                for (int r = 0; r < world; r++) same = same && all[(size_t)r * (KMAX + 2)] == K;
+                std::vector<int64_t> &dst = which ? c->piece_rows_all2 : c->piece_rows_all;
+                int &Kd = which ? c->pieces2 : c->pieces;
+                if (same) {
+                        Kd = K;
+                        dst.assign((size_t)world * (K + 1), 0);
+                        for (int r = 0; r < world; r++)
+                                for (int k = 0; k <= K; k++)
+                                        dst[(size_t)r * (K + 1) + k] = all[(size_t)r * (KMAX + 2) + 1 + k];
+                } else {
+                        Kd = 1;
+                        single_piece(&op);
+                        dst.assign((size_t)world * 2, 0);
+                        const std::vector<int64_t> &off = which ? c->n_off : c->m_off;
+                        for (int r = 0; r < world; r++) dst[(size_t)r * 2 + 1] = off[r + 1] - off[r];
+                }
+        }
+        return 0;
+}
+
+// all ranks take the same path: true only if `mine` holds on every rank
+int agree_flag(blk_ctx *c, bool mine, bool *all)
+{
+        Scratch tmp;
+        unsigned long long *flag = nullptr, h = mine ? 1ull : 0ull;
+        if (tmp.alloc(&flag, sizeof(h))) return 1;
+        CU(cudaMemcpyAsync(flag, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+        NC(g_nccl.AllReduce(flag, flag, 1, ncclUint64, ncclSum, c->comm, c->stream));
+        CU(cudaMemcpyAsync(&h, flag, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        *all = h == (unsigned long long)c->world;
+        return 0;
+}
+
+// Map every rank's tmp and Av_full into this rank's address space: raw pointers + peer access when the owner
+// lives in this process (one thread per GPU), CUDA IPC handles otherwise (one process per GPU).
+int setup_peers(blk_ctx *c, bool *ok_all)
+{
+        struct Record {
+                int32_t pid, device;
+                unsigned long long tmp, av;
+                cudaIpcMemHandle_t h_tmp, h_av;
+        };
+        const int world = c->world;
+        Record mine;
+        memset(&mine, 0, sizeof(mine));
+        mine.pid = (int32_t)getpid(); mine.device = c->device;
+        mine.tmp = (unsigned long long)(uintptr_t)c->tmp; mine.av = (unsigned long long)(uintptr_t)c->Av_full;
+        const bool ipc_ok = cudaIpcGetMemHandle(&mine.h_tmp, c->tmp) == cudaSuccess &&
+                            cudaIpcGetMemHandle(&mine.h_av, c->Av_full) == cudaSuccess;
+        cudaGetLastError();
+        Scratch tmp;
+        unsigned char *dh = nullptr;
+        if (tmp.alloc(&dh, sizeof(Record) * world)) return 1;
+        CU(cudaMemcpyAsync(dh + sizeof(Record) * c->rank, &mine, sizeof(Record), cudaMemcpyHostToDevice, c->stream));
+        NC(g_nccl.AllGather(dh + sizeof(Record) * c->rank, dh, sizeof(Record), ncclUint8, c->comm, c->stream));
+        std::vector<Record> all(world);
+        CU(cudaMemcpyAsync(all.data(), dh, sizeof(Record) * world, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        bool ok = true;
+        c->peer_tmp.assign(world, nullptr); c->peer_av.assign(world, nullptr); c->peer_ipc.assign(world, 0);
+        c->peer_tmp[c->rank] = c->tmp; c->peer_av[c->rank] = c->Av_full;
+        for (int r = 0; r < world && ok; r++) {
+                if (r == c->rank) continue;
+                if (all[r].pid == mine.pid) {
+                        int can = 0;
+                        ok = all[r].device != c->device && cudaDeviceCanAccessPeer(&can, c->device, all[r].device) == cudaSuccess && can;
+                        if (ok) {
+                                cudaError_t e = cudaDeviceEnablePeerAccess(all[r].device, 0);
+                                ok = e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled;
+                        }
+                        c->peer_tmp[r] = (u32 *)(uintptr_t)all[r].tmp; c->peer_av[r] = (u32 *)(uintptr_t)all[r].av;
+                } else {
+                        void *a = nullptr, *b = nullptr;
+                        ok = ipc_ok && cudaIpcOpenMemHandle(&a, all[r].h_tmp, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+                        if (ok) {
+                                c->peer_tmp[r] = (u32 *)a; c->peer_ipc[r] = 1;
+                                ok = cudaIpcOpenMemHandle(&b, all[r].h_av, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+                                if (ok) c->peer_av[r] = (u32 *)b;
+                        }
+                }
+        }
+        cudaGetLastError();            // a refused mapping must not poison later calls
+        return agree_flag(c, ok, ok_all);
+}
+
+void close_peers(blk_ctx *c)
+{
+        for (int r = 0; r < (int)c->peer_ipc.size(); r++) {
+                if (r == c->rank || !c->peer_ipc[r]) continue;
+                if (c->peer_tmp[r]) cudaIpcCloseMemHandle(c->peer_tmp[r]);
+                if (c->peer_av[r]) cudaIpcCloseMemHandle(c->peer_av[r]);
+        }
+        c->peer_tmp.clear(); c->peer_av.clear(); c->peer_ipc.clear();
+}
+
+// the multi-GPU part of blk_create: communicator, pieces, side stream, the recurrence blocks, the exchange mode
+int create_multi(blk_ctx *c, const blk_params *prm, bool grid_req)
+{
+        const int world = c->world, np = c->geo.np;
+        std::string why;
+        if (!nccl_load(&why)) return fail(why);
+        ncclUniqueId id;
+        memcpy(&id, prm->nccl_id, sizeof(id));
+        NC(g_nccl.CommInitRank(&c->comm, world, id, c->rank));
+        const char *e = getenv("BLK_ALLGATHER");
+        if (!(e && e[0] == 'b')) c->nccl_allgather = g_nccl.AllGather;     // BLK_ALLGATHER=bcast forces broadcasts
+        if (agree_pieces(c)) return 1;
+        if (c->colblocks) {
+                // arrival-order mode: pieces are equal row counts, known on every rank without an exchange
+                const int K = c->colblocks;
+                c->pieces = c->pieces2 = K;
+                c->piece_rows_all.assign((size_t)world * (K + 1), 0);
+                c->piece_rows_all2.assign((size_t)world * (K + 1), 0);
+                for (int r = 0; r < world; r++)
+                        for (int q = 0; q <= K; q++) {
+                                c->piece_rows_all[(size_t)r * (K + 1) + q] = (c->m_off[r + 1] - c->m_off[r]) * q / K;
+                                c->piece_rows_all2[(size_t)r * (K + 1) + q] = (c->n_off[r + 1] - c->n_off[r]) * q / K;
+                        }
+                c->ev_arrived.resize((size_t)2 * K);
+                for (auto &ev : c->ev_arrived) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                CU(cudaEventCreateWithFlags(&c->ev_aux, cudaEventDisableTiming));
+        }
+        {
+                // highest priority: the block scheduler then places the exchange's few CTAs ahead of the thousands
+                // of queued SpMV blocks instead of after them
+                int pr_least = 0, pr_greatest = 0;
+                CU(cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest));
+                CU(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, pr_greatest));
+                c->ev_piece.resize(std::max(c->pieces, c->pieces2));
+                for (auto &ev : c->ev_piece) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                CU(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
+        }
+        const char *er = getenv("BLK_RECUR");
+        if ((er && er[0] == '0') || grid_req) return 0;
+
+        c->mg_recur = true;
+        const int64_t lm = c->m1() - c->m0();
+        const size_t bav = sizeof(u32) * (size_t)gather_cap(c->n_off) * np;
+        const size_t blm = sizeof(u32) * (size_t)(lm > 0 ? lm : 1) * np;
+        CU(cudaMalloc(&c->Av_full, bav));
+        CU(cudaMemsetAsync(c->Av_full, 0, bav, c->stream));
+        cudaFree(c->Av);
+        c->Av = c->Av_full + (size_t)c->n0() * np;
+        CU(cudaMalloc(&c->Tp, blm)); CU(cudaMalloc(&c->U, blm));
+        CU(cudaMemsetAsync(c->Tp, 0, blm, c->stream));
+        CU(cudaMemsetAsync(c->U, 0, blm, c->stream));
+        if (c->Mc > c->N) { CU(cudaMalloc(&c->tmp_prev, blm)); CU(cudaMemsetAsync(c->tmp_prev, 0, blm, c->stream)); }
+        c->block_bytes += bav + 3 * blm;
+        CU(cudaStreamSynchronize(c->stream));
+
+        // ---- how Av and the new tmp travel.  Default: our own stores over NVLink
+        // (XCH_PUSH) when every rank could map every peer's blocks; BLK_EXCHANGE=nccl | ce | push selects.
+        // Measured on 8 x B200, config 4 (profiles/): see DESIGN.md.
+        int want = blk_ctx::XCH_PUSH;
+        if (const char *ex = getenv("BLK_EXCHANGE")) {
+                if (!strcmp(ex, "nccl")) want = blk_ctx::XCH_NCCL;
+                else if (!strcmp(ex, "ce")) want = blk_ctx::XCH_CE;
+                else if (!strcmp(ex, "push")) want = blk_ctx::XCH_PUSH;
+                else return fail("BLK_EXCHANGE must be nccl, ce or push");
+        } else if (env_flag("BLK_P2P")) want = blk_ctx::XCH_CE;           // round-1 spelling
+        if (np < 4 || c->colblocks) want = blk_ctx::XCH_NCCL;          // rows shorter than 16 bytes / arrival-order mode
+        if (want != blk_ctx::XCH_NCCL) {
+                bool ok = false;
+                if (setup_peers(c, &ok)) return 1;
+                if (!ok) { close_peers(c); want = blk_ctx::XCH_NCCL; }
+        }
+        c->xch = want;
+        if (const char *ea = getenv("BLK_PUSH_AV")) c->push_av_in_spmv = strcmp(ea, "kernel") != 0;     // kernel | spmv
+        if (const char *ec = getenv("BLK_PUSH_CTAS")) c->push_ctas = std::max(1, std::min(1024, atoi(ec)));
+        if (c->xch != blk_ctx::XCH_NCCL) {
+                CU(cudaMalloc(&c->barrier_word, sizeof(u64)));
+                CU(cudaMemsetAsync(c->barrier_word, 0, sizeof(u64), c->stream));
+        }
+        if (c->xch == blk_ctx::XCH_CE) {
+                c->copy_streams.resize(world - 1); c->ev_copies.resize(world - 1);
+                for (auto &st : c->copy_streams) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+                for (auto &ev : c->ev_copies) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        }
+        CU(cudaStreamSynchronize(c->stream));
+        return 0;
+}
+
+int create_impl(blk_ctx *c, const blk_params *prm)
+{
+        const int world = c->world, np = c->geo.np;
+        const ModP &m = c->m;
+        // Paths that have been validated on GPUs but are not the default need an explicit opt-in next to
+        // their own switch, so that a stray environment variable cannot reroute a production run.
+        const bool experimental = env_flag("BLK_EXPERIMENTAL");
+        {
+                // column-blocked products (world == 1: a test mode that exercises the blocks and the combine kernel
+                // under the whole single-GPU test suite; world > 1: arrival-order exchange)
+                const char *e = getenv("BLK_COLBLOCKS");
+                int K = e ? atoi(e) : 0;
+                if (K != 0 && !experimental) return fail("BLK_COLBLOCKS is an experimental mode: set BLK_EXPERIMENTAL=1 as well");
+                const char *er = getenv("BLK_RECUR");
+                if (K >= 2 && K <= 16 && !(world > 1 && er && er[0] == '0')) c->colblocks = K;
+        }
+        // BLK_GRID=PxQ or BLK_GRID=auto runs the loop on the P x Q block grid (world > 1 only)
+        bool grid_req = false;
+        int gridP = 0, gridQ = 0;
+        {
+                const char *e = getenv("BLK_GRID");
+                if (e && e[0] && world > 1) {
+                        if (!experimental) return fail("BLK_GRID is an experimental mode: set BLK_EXPERIMENTAL=1 as well");
+                        grid_req = true;
+                        if (sscanf(e, "%dx%d", &gridP, &gridQ) != 2) gridP = gridQ = 0;      // "auto": like MPI_Dims_create
+                        c->colblocks = 0;
+                }
+        }
+        std::vector<u32> grid_cntN, grid_cntM;
+        if (prm->stream) c->stream = (cudaStream_t)prm->stream;
+        else { CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+
+        dense_prepare(c->geo, c->m);
+
+        // ---- COO on the device
+        const int64_t nnz = prm->nnz;
+        Scratch coo;
+        int32_t *di = nullptr, *dj = nullptr;
+        u32 *dx = nullptr;
+        if (prm->coo_on_device || nnz == 0) {
+                di = (int32_t *)prm->Mi; dj = (int32_t *)prm->Mj; dx = (u32 *)prm->Mx;
+        } else {
+                if (coo.alloc(&di, sizeof(int32_t) * (size_t)nnz) || coo.alloc(&dj, sizeof(int32_t) * (size_t)nnz) ||
+                    coo.alloc(&dx, sizeof(u32) * (size_t)nnz))
+                        return 1;
+                CU(cudaMemcpyAsync(di, prm->Mi, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
+                CU(cudaMemcpyAsync(dj, prm->Mj, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
+                CU(cudaMemcpyAsync(dx, prm->Mx, sizeof(u32) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
+        }
+
+        // Lanczos-dimension index array and the other one
+        const int32_t *idxN = c->right ? dj : di;     // indexes rows of v/Av/p
+        const int32_t *idxM = c->right ? di : dj;     // indexes rows of tmp
+
+        // ---- row partitions
+        c->n_off.assign(world + 1, 0); c->m_off.assign(world + 1, 0);
+        c->n_off[world] = c->N; c->m_off[world] = c->Mc;
+        if (world > 1) {
+                for (int pass = 0; pass < 2; pass++) {
+                        std::vector<u32> hc;
+                        if (count_dimension(c, nnz, pass ? idxM : idxN, pass ? c->Mc : c->N, &hc)) return 1;
+                        (pass ? c->m_off : c->n_off) = partition_rows(hc, world);
+                        if (grid_req) (pass ? grid_cntM : grid_cntN).swap(hc);
+                }
+        }
+
+        // ---- degree-sorted labels for the N dimension + L2-resident hot prefix (single GPU)
+        {
+                const char *e = getenv("BLK_HOT"), *emin = getenv("BLK_HOT_MIN_BYTES"), *eb = getenv("BLK_HOT_BYTES");
+                cudaDeviceProp prop;
+                CU(cudaGetDeviceProperties(&prop, c->device));
+                long long min_bytes = emin ? atoll(emin) : 96ll << 20;
+                long long hot_bytes = eb ? atoll(eb) : 24ll << 20;
+                bool on = world == 1 && !c->colblocks && !(e && e[0] == '0') && np >= 4 && nnz > 0 &&
+                          (long long)c->N * np * 4 > min_bytes && hot_bytes > 0;
+                if (on) {
+                        std::string err = degree_sort_maps(nnz, idxN, c->N, &c->n_old2new, &c->n_new2old, c->stream);
+                        if (!err.empty()) return fail(err);
+                        c->hot_rows = std::min<int64_t>(c->N, hot_bytes / (4 * np));
+                        // B200's L2 is two halves (one per die) and lines gathered by SMs of both dies live
+                        // in both, so the set-aside has to hold the hot prefix twice.  (A device-wide limit: the
+                        // one piece of process state this library changes; restored by blk_destroy.)
+                        const char *ep = getenv("BLK_L2_PERSIST");
+                        long long persist = ep ? atoll(ep) : std::min<long long>(prop.persistingL2CacheMaxSize, 2 * hot_bytes);
+                        size_t before = 0;
+                        if (cudaDeviceGetLimit(&before, cudaLimitPersistingL2CacheSize) == cudaSuccess) {
+                                c->l2_persist_before = (long long)before;
+                                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)persist);
+                        }
+                        cudaGetLastError();
+                }
+        }
+
+        // ---- the two operators.  S1: rows = my block of the Mc dimension, columns = N dimension;
+        //      S2: rows = my block of the N dimension, columns = Mc dimension.
+        int want_pieces = 1;
+        if (world > 1) {
+                const char *e = getenv("BLK_PIECES");
+                // a piece should be worth >= ~0.5 ms of product time (about 25M entries); <= 4 pieces by default
+                long long per_rank = (long long)(nnz / world);
+                want_pieces = e ? atoi(e) : (int)std::max(1ll, std::min(4ll, per_rank / 25000000ll));
+                if (want_pieces < 1) want_pieces = 1;
+                if (want_pieces > 32) want_pieces = 32;
+        }
+        for (int which = 0; which < 2; which++) {
+                SpOp *op = which ? &c->S2 : &c->S1;
+                const int32_t *rk = which ? idxN : idxM, *ck = which ? idxM : idxN;
+                int64_t lo = which ? c->n0() : c->m0(), hi = which ? c->n1() : c->m1();
+                int64_t cols = which ? c->Mc : c->N;
+                std::string err;
+                if (world == 1) {
+                        err = build_operator(op, c->geo, prm->chunk_len, hi - lo, cols, lo, nnz, rk, ck, dx, m.p,
+                                             which ? c->n_old2new : nullptr, which ? nullptr : c->n_old2new, 1, c->stream);
+                        if (!which) op->hot_cols = (u32)c->hot_rows;
+                        if (err.empty() && c->colblocks &&
+                            build_colops(c, which ? &c->cb2 : &c->cb1, c->colblocks, prm->chunk_len, nnz, rk, ck, dx, lo, hi, cols,
+                                         which ? c->m_off : c->n_off))
+                                return 1;
+                } else {
+                        Scratch sel_buf;
+                        int32_t *sr = nullptr, *sc = nullptr; u32 *sx = nullptr;
+                        unsigned long long *cnt = nullptr, hcnt = 0;
+                        // upper bound of the selection is not known: count first
+                        std::vector<u32> hc;
+                        if (count_dimension(c, nnz, rk, which ? c->N : c->Mc, &hc)) return 1;
+                        int64_t sel = 0;
+                        for (int64_t r = lo; r < hi; r++) sel += hc[(size_t)r];
+                        std::vector<u32>().swap(hc);
+                        if (sel_buf.alloc(&cnt, sizeof(unsigned long long)) || sel_buf.alloc(&sr, sizeof(int32_t) * (size_t)sel) ||
+                            sel_buf.alloc(&sc, sizeof(int32_t) * (size_t)sel) || sel_buf.alloc(&sx, sizeof(u32) * (size_t)sel))
+                                return 1;
+                        CU(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
+                        if (nnz) k_select_range<<<nb(nnz), 256, 0, c->stream>>>(nnz, rk, ck, dx, lo, hi, sr, sc, sx, cnt);
+                        CU(cudaMemcpyAsync(&hcnt, cnt, sizeof(hcnt), cudaMemcpyDeviceToHost, c->stream));
+                        CU(cudaStreamSynchronize(c->stream));
+                        if ((int64_t)hcnt != sel) err = "shard selection count mismatch";
+                        else err = build_operator(op, c->geo, prm->chunk_len, hi - lo, cols, lo, sel, sr, sc, sx, m.p, nullptr, nullptr,
+                                                       want_pieces, c->stream);
+                        if (err.empty() && c->colblocks &&
+                            build_colops(c, which ? &c->cb2 : &c->cb1, c->colblocks, prm->chunk_len, sel, sr, sc, sx, lo, hi, cols,
+                                         which ? c->m_off : c->n_off))
+                                return 1;
+                }
+                if (!err.empty()) return fail(err);
+        }
+        CU(cudaStreamSynchronize(c->stream));
+        if (!grid_req) { coo.release(di); coo.release(dj); coo.release(dx); }     // the grid mode extracts its block later
+
+        // ---- vector blocks and the small working set
+        int64_t ln = c->n1() - c->n0();
+        size_t bv = sizeof(u32) * (size_t)gather_cap(c->n_off) * np, bt = sizeof(u32) * (size_t)gather_cap(c->m_off) * np;
+        size_t bl = sizeof(u32) * (size_t)(ln > 0 ? ln : 1) * np;
+        CU(cudaMalloc(&c->v, bv)); CU(cudaMalloc(&c->tmp, bt));
+        CU(cudaMalloc(&c->Av, bl)); CU(cudaMalloc(&c->p, bl));
+        CU(cudaMemsetAsync(c->v, 0, bv, c->stream)); CU(cudaMemsetAsync(c->tmp, 0, bt, c->stream));
+        CU(cudaMemsetAsync(c->Av, 0, bl, c->stream)); CU(cudaMemsetAsync(c->p, 0, bl, c->stream));
+        c->block_bytes = bv + bt + 2 * bl;
+        if (c->colblocks) {
+                int64_t lm_ = c->m1() - c->m0();
+                c->zstride = (size_t)std::max<int64_t>(1, std::max(ln, lm_)) * np;
+                CU(cudaMalloc(&c->zbuf, sizeof(u32) * c->zstride * c->colblocks));
+                CU(cudaMemsetAsync(c->zbuf, 0, sizeof(u32) * c->zstride * c->colblocks, c->stream));
+                c->block_bytes += sizeof(u32) * c->zstride * c->colblocks;
+        }
+        // staging for host <-> device block copies that need repacking (n < n_pad, relabelled rows): two slots
+        // so that the PCIe copy of one chunk overlaps the repacking kernel of the other
+        CU(cudaMalloc(&c->stage, 2 * blk_ctx::STAGE_BYTES));
+        c->block_bytes += 2 * blk_ctx::STAGE_BYTES;
+        c->dots_blocks = dots_num_blocks(ln, np);
+        CU(cudaMalloc(&c->mats, sizeof(u32) * mats_words(np)));
+        CU(cudaMalloc(&c->sums, sizeof(u64) * (size_t)2 * np * np));
+        CU(cudaMalloc(&c->state, sizeof(DevSmall)));
+        CU(cudaMalloc(&c->dots_counter, sizeof(unsigned)));
+        CU(cudaMemsetAsync(c->dots_counter, 0, sizeof(unsigned), c->stream));
+        {
+                const char *e = getenv("BLK_FUSE_SMALL");
+                c->fuse_small = world == 1 && np <= 32 && !(e && e[0] == '0');
+        }
+        c->check = env_flag("BLK_CHECK");
+        if (const char *ef = getenv("BLK_CHECK_FAULT")) c->check_fault = atoi(ef);
+        CU(cudaMallocHost(&c->h_state, sizeof(DevSmall)));
+        CU(cudaMemsetAsync(c->mats, 0, sizeof(u32) * mats_words(np), c->stream));
+        CU(cudaMemsetAsync(c->sums, 0, sizeof(u64) * (size_t)2 * np * np, c->stream));
+        memset(c->h_state, 0, sizeof(DevSmall));
+        c->h_state->halt = 1;
+        c->h_state->check = c->check ? 1 : 0;
+        c->h_state->fault_iter = c->check_fault;
+        if (push_state(c)) return 1;
+        CU(cudaStreamSynchronize(c->stream));
+
+        if (world > 1) {
+                if (create_multi(c, prm, grid_req)) return 1;
+                if (grid_req && grid_create(c, gridP, gridQ, prm->chunk_len, nnz, idxN, idxM, dx, grid_cntN, grid_cntM)) return 1;
+        }
+        return 0;
+}
+
+}  // namespace
+
+// blk_params.rank == BLK_RANK_ALL: one process, `world` GPUs (devices prm->device ... prm->device + world - 1)
+static int group_create(blk_ctx **out, const blk_params *prm, int world, int ndev)
+{
+        if (prm->device < 0 || prm->device + world > ndev) return fail("not enough CUDA devices for the requested number of GPUs");
+        if (world == 1) {
+                blk_params one = *prm;
+                one.rank = 0; one.world = 1;
+                return blk_create(out, &one);
+        }
+        unsigned char id[BLK_NCCL_ID_BYTES];
+        if (blk_nccl_unique_id(id)) return 1;
+        blk_ctx *g = new blk_ctx();
+        g->geo = make_geometry(prm->n);
+        modp_make(&g->m, prm->prime);
+        g->device = prm->device; g->rank = BLK_RANK_ALL; g->world = world; g->right = prm->right_kernel ? 1 : 0;
+        g->nrows = prm->nrows; g->ncols = prm->ncols;
+        g->N = g->right ? prm->ncols : prm->nrows;
+        g->Mc = g->right ? prm->nrows : prm->ncols;
+        g->members.assign((size_t)world, nullptr);
+        int rc = group_run(g, [&](blk_ctx *, int r) -> int {
+                blk_params p2 = *prm;
+                p2.rank = r; p2.world = world; p2.device = prm->device + r; p2.nccl_id = id; p2.stream = nullptr;
+                Scratch coo;
+                if (prm->coo_on_device && prm->nnz > 0 && p2.device != prm->device) {
+                        // the triplets live on the first GPU: every other member works on its own copy
+                        CU(cudaSetDevice(p2.device));
+                        int32_t *di = nullptr, *dj = nullptr;
+                        u32 *dx = nullptr;
+                        const size_t cnt = (size_t)prm->nnz;
+                        if (coo.alloc(&di, sizeof(int32_t) * cnt) || coo.alloc(&dj, sizeof(int32_t) * cnt) || coo.alloc(&dx, sizeof(u32) * cnt)) return 1;
+                        CU(cudaMemcpyPeer(di, p2.device, prm->Mi, prm->device, sizeof(int32_t) * cnt));
+                        CU(cudaMemcpyPeer(dj, p2.device, prm->Mj, prm->device, sizeof(int32_t) * cnt));
+                        CU(cudaMemcpyPeer(dx, p2.device, prm->Mx, prm->device, sizeof(u32) * cnt));
+                        p2.Mi = di; p2.Mj = dj; p2.Mx = dx;
+                }
+                return blk_create(&g->members[(size_t)r], &p2);
+        });
+        if (rc) {
+                std::string why = g_err;
+                blk_destroy(g);
+                return fail(why);
+        }
+        *out = g;
+        return 0;
+}
+
+int blk_create(blk_ctx **out, const blk_params *prm)
+{
+        if (!out) return fail("blk_create: null output pointer");
+        *out = nullptr;
+        if (!prm || prm->abi_version != BLK_ABI_VERSION) return fail("blk_params.abi_version mismatch");
+        if (prm->n < 1 || prm->n > BLK_MAX_N) return fail("blocking factor n must be in [1,64]");
+        if (prm->nrows < 1 || prm->ncols < 1 || prm->nnz < 0) return fail("bad matrix dimensions");
+        if (prm->nnz > 0 && (!prm->Mi || !prm->Mj || !prm->Mx)) return fail("null COO arrays");
+        int world = prm->world > 0 ? prm->world : 1;
+        ModP m;
+        if (!modp_make(&m, prm->prime)) return fail("prime must satisfy 2 <= p < 2^31");
+        int ndev = 0;
+        cudaError_t e0 = cudaGetDeviceCount(&ndev);
+        if (e0 != cudaSuccess || ndev == 0)
+                return fail(std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e0));
+        if (prm->rank == BLK_RANK_ALL) return group_create(out, prm, world, ndev);
+        if (prm->rank < 0 || prm->rank >= world) return fail("rank out of range");
+        if (world > 1 && !prm->nccl_id) return fail("world > 1 needs blk_params.nccl_id");
+        if (prm->device < 0 || prm->device >= ndev) return fail("device ordinal out of range");
+        CU(cudaSetDevice(prm->device));
+
+        blk_ctx *c = new blk_ctx();
+        c->geo = make_geometry(prm->n);
+        c->m = m;
+        c->device = prm->device; c->rank = prm->rank; c->world = world; c->right = prm->right_kernel ? 1 : 0;
+        c->nrows = prm->nrows; c->ncols = prm->ncols;
+        c->N = c->right ? prm->ncols : prm->nrows;
+        c->Mc = c->right ? prm->nrows : prm->ncols;
+        c->use_graph = prm->use_graph;
+        if (create_impl(c, prm)) {
+                std::string why = g_err;          // blk_destroy must not lose the reason
+                blk_destroy(c);
+                return fail(why);
+        }
+        *out = c;
+        return 0;
+}
+
+
 // ---------------------------------------------------------------------------------- C ABI
 extern "C" {
 
@@ -1228,10 +1873,24 @@ int64_t blk_block_pad(int32_t nrows, int32_t ncols, int32_t n, int32_t right_ker
 int blk_destroy(blk_ctx *c)
 {
         if (!c) return 0;
+        if (c->is_group()) {
+                group_run(c, [](blk_ctx *mem, int) { return blk_destroy(mem); });
+                delete c;
+                return 0;
+        }
         cudaSetDevice(c->device);
         if (c->stream) cudaStreamSynchronize(c->stream);
+        if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
         destroy_graph(c);
         grid_destroy(c);
+        if (!c->peer_tmp.empty()) {
+                // peers hold mappings of this rank's blocks (and this rank of theirs): unmap, then meet, then free
+                close_peers(c);
+                if (c->comm && c->barrier_word && c->stream) {
+                        g_nccl.AllReduce(c->barrier_word, c->barrier_word, 1, ncclUint64, ncclSum, c->comm, c->stream);
+                        cudaStreamSynchronize(c->stream);
+                }
+        }
         if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
         free_operator(&c->S1);
         free_operator(&c->S2);
@@ -1244,12 +1903,8 @@ int blk_destroy(blk_ctx *c)
         cudaFree(c->Tp); cudaFree(c->U); cudaFree(c->tmp_prev);
         cudaFree(c->mats); cudaFree(c->sums); cudaFree(c->state); cudaFree(c->dots_counter);
         cudaFree(c->n_old2new); cudaFree(c->n_new2old);
+        cudaFree(c->stage);
         if (c->h_state) cudaFreeHost(c->h_state);
-        for (int r = 0; r < (int)c->peer_tmp.size(); r++) {
-                if (r == c->rank) continue;
-                if (c->peer_tmp[r]) cudaIpcCloseMemHandle(c->peer_tmp[r]);
-                if (c->peer_av[r]) cudaIpcCloseMemHandle(c->peer_av[r]);
-        }
         for (auto e : c->ev_copies) cudaEventDestroy(e);
         for (auto st : c->copy_streams) cudaStreamDestroy(st);
         cudaFree(c->barrier_word);
@@ -1257,395 +1912,26 @@ int blk_destroy(blk_ctx *c)
         if (c->ev_comm) cudaEventDestroy(c->ev_comm);
         if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
         if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+        if (c->l2_persist_before >= 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)c->l2_persist_before);
+        cudaGetLastError();
         delete c;
         return 0;
 }
 
-int blk_create(blk_ctx **out, const blk_params *prm)
-{
-        *out = nullptr;
-        if (!prm || prm->abi_version != BLK_ABI_VERSION) return fail("blk_params.abi_version mismatch");
-        if (prm->n < 1 || prm->n > BLK_MAX_N) return fail("blocking factor n must be in [1,64]");
-        if (prm->nrows < 1 || prm->ncols < 1 || prm->nnz < 0) return fail("bad matrix dimensions");
-        if (prm->nnz > 0 && (!prm->Mi || !prm->Mj || !prm->Mx)) return fail("null COO arrays");
-        int world = prm->world > 0 ? prm->world : 1;
-        if (prm->rank < 0 || prm->rank >= world) return fail("rank out of range");
-        if (world > 1 && !prm->nccl_id) return fail("world > 1 needs blk_params.nccl_id");
-        ModP m;
-        if (!modp_make(&m, prm->prime)) return fail("prime must satisfy 2 <= p < 2^31");
-        int ndev = 0;
-        cudaError_t e0 = cudaGetDeviceCount(&ndev);
-        if (e0 != cudaSuccess || ndev == 0)
-                return fail(std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e0));
-        if (prm->device < 0 || prm->device >= ndev) return fail("device ordinal out of range");
-        CU(cudaSetDevice(prm->device));
-
-        blk_ctx *c = new blk_ctx();
-        c->geo = make_geometry(prm->n);
-        c->m = m;
-        c->device = prm->device; c->rank = prm->rank; c->world = world; c->right = prm->right_kernel ? 1 : 0;
-        c->nrows = prm->nrows; c->ncols = prm->ncols;
-        c->N = c->right ? prm->ncols : prm->nrows;
-        c->Mc = c->right ? prm->nrows : prm->ncols;
-        c->use_graph = prm->use_graph;
-        {
-                // experimental: column-blocked products (world == 1: a test mode that exercises the blocks and the
-                // combine kernel under the whole single-GPU test suite; world > 1: arrival-order exchange)
-                const char *e = getenv("BLK_COLBLOCKS");
-                int K = e ? atoi(e) : 0;
-                const char *er = getenv("BLK_RECUR"), *ep = getenv("BLK_P2P");
-                if (K >= 2 && K <= 16 && !(world > 1 && ((er && er[0] == '0') || (ep && ep[0] == '1')))) c->colblocks = K;
-        }
-        // experimental: BLK_GRID=PxQ or BLK_GRID=auto runs the loop on the P x Q block grid (world > 1 only)
-        bool grid_req = false;
-        int gridP = 0, gridQ = 0;
-        {
-                const char *e = getenv("BLK_GRID");
-                if (e && e[0] && world > 1) {
-                        grid_req = true;
-                        if (sscanf(e, "%dx%d", &gridP, &gridQ) != 2) gridP = gridQ = 0;      // "auto": like MPI_Dims_create
-                        c->colblocks = 0;
-                }
-        }
-        std::vector<u32> grid_cntN, grid_cntM;
-        const int np = c->geo.np;
-#define CUX(call)                                                                                  \
-        do {                                                                                       \
-                cudaError_t e_ = (call);                                                           \
-                if (e_ != cudaSuccess) {                                                           \
-                        fail(std::string(#call) + ": " + cudaGetErrorString(e_));                  \
-                        blk_destroy(c);                                                            \
-                        return 1;                                                                  \
-                }                                                                                  \
-        } while (0)
-        if (prm->stream) c->stream = (cudaStream_t)prm->stream;
-        else { CUX(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
-
-        dense_prepare(c->geo, c->m);
-
-        // ---- COO on the device
-        const int64_t nnz = prm->nnz;
-        int32_t *di = nullptr, *dj = nullptr;
-        u32 *dx = nullptr;
-        bool own_coo = false;
-        if (prm->coo_on_device || nnz == 0) {
-                di = (int32_t *)prm->Mi; dj = (int32_t *)prm->Mj; dx = (u32 *)prm->Mx;
-        } else {
-                own_coo = true;
-                CUX(cudaMalloc(&di, sizeof(int32_t) * (size_t)nnz));
-                CUX(cudaMalloc(&dj, sizeof(int32_t) * (size_t)nnz));
-                CUX(cudaMalloc(&dx, sizeof(u32) * (size_t)nnz));
-                CUX(cudaMemcpyAsync(di, prm->Mi, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
-                CUX(cudaMemcpyAsync(dj, prm->Mj, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
-                CUX(cudaMemcpyAsync(dx, prm->Mx, sizeof(u32) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
-        }
-        auto free_coo = [&]() { if (own_coo) { cudaFree(di); cudaFree(dj); cudaFree(dx); } };
-
-        // Lanczos-dimension index array and the other one
-        const int32_t *idxN = c->right ? dj : di;     // indexes rows of v/Av/p
-        const int32_t *idxM = c->right ? di : dj;     // indexes rows of tmp
-
-        // ---- row partitions
-        c->n_off.assign(world + 1, 0); c->m_off.assign(world + 1, 0);
-        c->n_off[world] = c->N; c->m_off[world] = c->Mc;
-        if (world > 1) {
-                for (int pass = 0; pass < 2; pass++) {
-                        int64_t dim = pass ? c->Mc : c->N;
-                        u32 *dc = nullptr;
-                        CUX(cudaMalloc(&dc, sizeof(u32) * (size_t)dim));
-                        CUX(cudaMemsetAsync(dc, 0, sizeof(u32) * (size_t)dim, c->stream));
-                        if (nnz) k_count_rows<<<nb(nnz), 256, 0, c->stream>>>(nnz, pass ? idxM : idxN, dim, dc);
-                        std::vector<u32> hc((size_t)dim);
-                        CUX(cudaMemcpyAsync(hc.data(), dc, sizeof(u32) * (size_t)dim, cudaMemcpyDeviceToHost, c->stream));
-                        CUX(cudaStreamSynchronize(c->stream));
-                        cudaFree(dc);
-                        (pass ? c->m_off : c->n_off) = partition_rows(hc, world);
-                        if (grid_req) (pass ? grid_cntM : grid_cntN) = hc;
-                }
-        }
-
-        // ---- degree-sorted labels for the N dimension + L2-resident hot prefix (single GPU)
-        {
-                const char *e = getenv("BLK_HOT"), *emin = getenv("BLK_HOT_MIN_BYTES"), *eb = getenv("BLK_HOT_BYTES");
-                cudaDeviceProp prop;
-                CUX(cudaGetDeviceProperties(&prop, c->device));
-                long long min_bytes = emin ? atoll(emin) : 96ll << 20;
-                long long hot_bytes = eb ? atoll(eb) : 24ll << 20;
-                bool on = world == 1 && !c->colblocks && !(e && e[0] == '0') && np >= 4 && nnz > 0 &&
-                          (long long)c->N * np * 4 > min_bytes && hot_bytes > 0;
-                if (on) {
-                        std::string err = degree_sort_maps(nnz, idxN, c->N, &c->n_old2new, &c->n_new2old, c->stream);
-                        if (!err.empty()) { free_coo(); fail(err); blk_destroy(c); return 1; }
-                        c->hot_rows = std::min<int64_t>(c->N, hot_bytes / (4 * np));
-                        // B200's L2 is two halves (one per die) and lines gathered by SMs of both dies live
-                        // in both, so the set-aside has to hold the hot prefix twice
-                        const char *ep = getenv("BLK_L2_PERSIST");
-                        long long persist = ep ? atoll(ep) : std::min<long long>(prop.persistingL2CacheMaxSize, 2 * hot_bytes);
-                        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)persist);
-                }
-        }
-
-        // ---- the two operators.  S1: rows = my block of the Mc dimension, columns = N dimension;
-        //      S2: rows = my block of the N dimension, columns = Mc dimension.
-        int want_pieces = 1;
-        if (world > 1) {
-                const char *e = getenv("BLK_PIECES");
-                // a piece should be worth >= ~0.5 ms of product time (about 25M entries); <= 4 pieces
-                // (8 x B200, config 4: 4 pieces 61.7 it/s, 8 pieces 58.1 it/s)
-                long long per_rank = (long long)(nnz / world);
-                want_pieces = e ? atoi(e) : (int)std::max(1ll, std::min(4ll, per_rank / 25000000ll));
-                if (want_pieces < 1) want_pieces = 1;
-                if (want_pieces > 32) want_pieces = 32;
-        }
-        for (int which = 0; which < 2; which++) {
-                SpOp *op = which ? &c->S2 : &c->S1;
-                const int32_t *rk = which ? idxN : idxM, *ck = which ? idxM : idxN;
-                int64_t lo = which ? c->n0() : c->m0(), hi = which ? c->n1() : c->m1();
-                int64_t cols = which ? c->Mc : c->N;
-                std::string err;
-                if (world == 1) {
-                        err = build_operator(op, c->geo, prm->chunk_len, hi - lo, cols, lo, nnz, rk, ck, dx, m.p,
-                                             which ? c->n_old2new : nullptr, which ? nullptr : c->n_old2new, 1, c->stream);
-                        if (!which) op->hot_cols = (u32)c->hot_rows;
-                        if (err.empty() && c->colblocks &&
-                            build_colops(c, which ? &c->cb2 : &c->cb1, c->colblocks, prm->chunk_len, nnz, rk, ck, dx, lo, hi, cols,
-                                         which ? c->m_off : c->n_off)) {
-                                free_coo(); blk_destroy(c); return 1;
-                        }
-                } else {
-                        int32_t *sr = nullptr, *sc = nullptr; u32 *sx = nullptr;
-                        unsigned long long *cnt = nullptr, hcnt = 0;
-                        // upper bound of the selection is not known: count first
-                        CUX(cudaMalloc(&cnt, sizeof(unsigned long long)));
-                        u32 *dc = nullptr;
-                        int64_t dim = which ? c->N : c->Mc;
-                        CUX(cudaMalloc(&dc, sizeof(u32) * (size_t)dim));
-                        CUX(cudaMemsetAsync(dc, 0, sizeof(u32) * (size_t)dim, c->stream));
-                        if (nnz) k_count_rows<<<nb(nnz), 256, 0, c->stream>>>(nnz, rk, dim, dc);
-                        std::vector<u32> hc((size_t)(hi - lo));
-                        if (hi > lo)
-                                CUX(cudaMemcpyAsync(hc.data(), dc + lo, sizeof(u32) * (size_t)(hi - lo), cudaMemcpyDeviceToHost, c->stream));
-                        CUX(cudaStreamSynchronize(c->stream));
-                        cudaFree(dc);
-                        int64_t sel = 0;
-                        for (u32 q : hc) sel += q;
-                        int64_t cap = sel > 0 ? sel : 1;
-                        CUX(cudaMalloc(&sr, sizeof(int32_t) * (size_t)cap));
-                        CUX(cudaMalloc(&sc, sizeof(int32_t) * (size_t)cap));
-                        CUX(cudaMalloc(&sx, sizeof(u32) * (size_t)cap));
-                        CUX(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
-                        if (nnz) k_select_range<<<nb(nnz), 256, 0, c->stream>>>(nnz, rk, ck, dx, lo, hi, sr, sc, sx, cnt);
-                        CUX(cudaMemcpyAsync(&hcnt, cnt, sizeof(hcnt), cudaMemcpyDeviceToHost, c->stream));
-                        CUX(cudaStreamSynchronize(c->stream));
-                        cudaFree(cnt);
-                        if ((int64_t)hcnt != sel) err = "shard selection count mismatch";
-                        else err = build_operator(op, c->geo, prm->chunk_len, hi - lo, cols, lo, sel, sr, sc, sx, m.p, nullptr, nullptr,
-                                                       want_pieces, c->stream);
-                        if (err.empty() && c->colblocks &&
-                            build_colops(c, which ? &c->cb2 : &c->cb1, c->colblocks, prm->chunk_len, sel, sr, sc, sx, lo, hi, cols,
-                                         which ? c->m_off : c->n_off)) {
-                                cudaFree(sr); cudaFree(sc); cudaFree(sx);
-                                free_coo(); blk_destroy(c); return 1;
-                        }
-                        cudaFree(sr); cudaFree(sc); cudaFree(sx);
-                }
-                if (!err.empty()) { free_coo(); fail(err); blk_destroy(c); return 1; }
-        }
-        CUX(cudaStreamSynchronize(c->stream));
-        if (!grid_req) free_coo();          // the grid mode extracts its block after the communicator exists
-
-        // ---- vector blocks and the small working set
-        int64_t ln = c->n1() - c->n0();
-        size_t bv = sizeof(u32) * (size_t)gather_cap(c->n_off) * np, bt = sizeof(u32) * (size_t)gather_cap(c->m_off) * np;
-        size_t bl = sizeof(u32) * (size_t)(ln > 0 ? ln : 1) * np;
-        CUX(cudaMalloc(&c->v, bv)); CUX(cudaMalloc(&c->tmp, bt));
-        CUX(cudaMalloc(&c->Av, bl)); CUX(cudaMalloc(&c->p, bl));
-        CUX(cudaMemsetAsync(c->v, 0, bv, c->stream)); CUX(cudaMemsetAsync(c->tmp, 0, bt, c->stream));
-        CUX(cudaMemsetAsync(c->Av, 0, bl, c->stream)); CUX(cudaMemsetAsync(c->p, 0, bl, c->stream));
-        c->block_bytes = bv + bt + 2 * bl;
-        if (c->colblocks) {
-                int64_t lm_ = c->m1() - c->m0();
-                c->zstride = (size_t)std::max<int64_t>(1, std::max(ln, lm_)) * np;
-                CUX(cudaMalloc(&c->zbuf, sizeof(u32) * c->zstride * c->colblocks));
-                CUX(cudaMemsetAsync(c->zbuf, 0, sizeof(u32) * c->zstride * c->colblocks, c->stream));
-                c->block_bytes += sizeof(u32) * c->zstride * c->colblocks;
-        }
-        c->dots_blocks = dots_num_blocks(ln, np);
-        CUX(cudaMalloc(&c->mats, sizeof(u32) * mats_words(np)));
-        CUX(cudaMalloc(&c->sums, sizeof(u64) * (size_t)2 * np * np));
-        CUX(cudaMalloc(&c->state, sizeof(DevSmall)));
-        CUX(cudaMalloc(&c->dots_counter, sizeof(unsigned)));
-        CUX(cudaMemsetAsync(c->dots_counter, 0, sizeof(unsigned), c->stream));
-        {
-                const char *e = getenv("BLK_FUSE_SMALL");
-                c->fuse_small = world == 1 && np <= 32 && !(e && e[0] == '0');
-        }
-        CUX(cudaMallocHost(&c->h_state, sizeof(DevSmall)));
-        CUX(cudaMemsetAsync(c->mats, 0, sizeof(u32) * mats_words(np), c->stream));
-        CUX(cudaMemsetAsync(c->sums, 0, sizeof(u64) * (size_t)2 * np * np, c->stream));
-        memset(c->h_state, 0, sizeof(DevSmall));
-        c->h_state->halt = 1;
-        if (push_state(c)) { blk_destroy(c); return 1; }
-        CUX(cudaStreamSynchronize(c->stream));
-
-        if (world > 1) {
-                std::string why;
-                if (!nccl_load(&why)) { fail(why); blk_destroy(c); return 1; }
-                ncclUniqueId id;
-                memcpy(&id, prm->nccl_id, sizeof(id));
-                ncclResult_t r = g_nccl.CommInitRank(&c->comm, world, id, c->rank);
-                if (r != ncclSuccess) {
-                        fail(std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
-                        blk_destroy(c);
-                        return 1;
-                }
-                const char *e = getenv("BLK_ALLGATHER");
-                if (!(e && e[0] == 'b')) c->nccl_allgather = g_nccl.AllGather;     // BLK_ALLGATHER=bcast forces broadcasts
-                // every rank needs every rank's piece boundaries of both operators
-                for (int which = 0; which < 2; which++) {
-                        const SpOp &op = which ? c->S2 : c->S1;
-                        const int KMAX = 32;
-                        std::vector<long long> mine(KMAX + 2, 0), all((size_t)(KMAX + 2) * world, 0);
-                        int K = (int)op.piece_tile.size() - 1;
-                        mine[0] = K;
-                        for (int k = 0; k <= K; k++) mine[1 + k] = op.piece_row[k];
-                        long long *dbuf = nullptr;
-                        CUX(cudaMalloc(&dbuf, sizeof(long long) * all.size()));
-                        CUX(cudaMemcpyAsync(dbuf + (size_t)c->rank * (KMAX + 2), mine.data(), sizeof(long long) * (KMAX + 2),
-                                            cudaMemcpyHostToDevice, c->stream));
-                        ncclResult_t r2 = g_nccl.AllGather(dbuf + (size_t)c->rank * (KMAX + 2), dbuf, (size_t)(KMAX + 2), ncclInt64,
-                                                            c->comm, c->stream);
-                        if (r2 != ncclSuccess) { fail(std::string("ncclAllGather: ") + g_nccl.GetErrorString(r2)); blk_destroy(c); return 1; }
-                        CUX(cudaMemcpyAsync(all.data(), dbuf, sizeof(long long) * all.size(), cudaMemcpyDeviceToHost, c->stream));
-                        CUX(cudaStreamSynchronize(c->stream));
-                        cudaFree(dbuf);
-                        bool same = true;
-                        for (int r = 0; r < world; r++) same = same && all[(size_t)r * (KMAX + 2)] == K;
-                        std::vector<int64_t> &dst = which ? c->piece_rows_all2 : c->piece_rows_all;
-                        int &Kd = which ? c->pieces2 : c->pieces;
-                        if (same) {
-                                Kd = K;
-                                dst.assign((size_t)world * (K + 1), 0);
-                                for (int r = 0; r < world; r++)
-                                        for (int k = 0; k <= K; k++)
-                                                dst[(size_t)r * (K + 1) + k] = all[(size_t)r * (KMAX + 2) + 1 + k];
-                        } else {                       // ranks disagree (tiny operators): one piece = the whole block
-                                Kd = 1;
-                                dst.assign((size_t)world * 2, 0);
-                                const std::vector<int64_t> &off = which ? c->n_off : c->m_off;
-                                for (int r = 0; r < world; r++) dst[(size_t)r * 2 + 1] = off[r + 1] - off[r];
-                        }
-                }
-                if (c->colblocks) {
-                        // arrival-order mode: pieces are equal row counts, known on every rank without an exchange
-                        const int K = c->colblocks;
-                        c->pieces = c->pieces2 = K;
-                        c->piece_rows_all.assign((size_t)world * (K + 1), 0);
-                        c->piece_rows_all2.assign((size_t)world * (K + 1), 0);
-                        for (int r = 0; r < world; r++)
-                                for (int q = 0; q <= K; q++) {
-                                        c->piece_rows_all[(size_t)r * (K + 1) + q] = (c->m_off[r + 1] - c->m_off[r]) * q / K;
-                                        c->piece_rows_all2[(size_t)r * (K + 1) + q] = (c->n_off[r + 1] - c->n_off[r]) * q / K;
-                                }
-                        c->ev_arrived.resize((size_t)2 * K);
-                        for (auto &ev : c->ev_arrived) CUX(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-                        CUX(cudaEventCreateWithFlags(&c->ev_aux, cudaEventDisableTiming));
-                }
-                {
-                        // highest priority: the block scheduler then places NCCL's few large CTAs ahead
-                        // of the thousands of queued SpMV blocks instead of after them
-                        int pr_least = 0, pr_greatest = 0;
-                        CUX(cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest));
-                        CUX(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, pr_greatest));
-                        c->ev_piece.resize(std::max(c->pieces, c->pieces2));
-                        for (auto &ev : c->ev_piece) CUX(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-                        CUX(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
-                }
-                const char *er = getenv("BLK_RECUR");
-                if (!(er && er[0] == '0') && !grid_req) {
-                        c->mg_recur = true;
-                        int64_t lm = c->m1() - c->m0();
-                        size_t bav = sizeof(u32) * (size_t)gather_cap(c->n_off) * np;
-                        size_t blm = sizeof(u32) * (size_t)(lm > 0 ? lm : 1) * np;
-                        CUX(cudaMalloc(&c->Av_full, bav));
-                        CUX(cudaMemsetAsync(c->Av_full, 0, bav, c->stream));
-                        cudaFree(c->Av);
-                        c->Av = c->Av_full + (size_t)c->n0() * np;
-                        CUX(cudaMalloc(&c->Tp, blm)); CUX(cudaMalloc(&c->U, blm));
-                        CUX(cudaMemsetAsync(c->Tp, 0, blm, c->stream));
-                        CUX(cudaMemsetAsync(c->U, 0, blm, c->stream));
-                        if (c->Mc > c->N) { CUX(cudaMalloc(&c->tmp_prev, blm)); CUX(cudaMemsetAsync(c->tmp_prev, 0, blm, c->stream)); }
-                        c->block_bytes += bav + 3 * blm;
-                        CUX(cudaStreamSynchronize(c->stream));
-                        // ---- one-sided pushes over NVLink: exchange IPC handles of tmp and Av_full
-                        // (measured on 8 x B200, config 4: NCCL broadcasts of 4 pieces 61.7 it/s, copy-engine
-                        // pushes 57.9 it/s -- so the pushes are opt-in: BLK_P2P=1)
-                        const char *ep = getenv("BLK_P2P");
-                        if (ep && ep[0] == '1') {
-                                struct Handles { cudaIpcMemHandle_t tmp, av; };
-                                static_assert(sizeof(Handles) == 128, "ipc handle size");
-                                Handles mine;
-                                bool ok = cudaIpcGetMemHandle(&mine.tmp, c->tmp) == cudaSuccess &&
-                                          cudaIpcGetMemHandle(&mine.av, c->Av_full) == cudaSuccess;
-                                unsigned char *dh = nullptr;
-                                CUX(cudaMalloc(&dh, sizeof(Handles) * world));
-                                CUX(cudaMemcpyAsync(dh + sizeof(Handles) * c->rank, &mine, sizeof(Handles), cudaMemcpyHostToDevice, c->stream));
-                                ncclResult_t r3 = g_nccl.AllGather(dh + sizeof(Handles) * c->rank, dh, sizeof(Handles), ncclUint8, c->comm, c->stream);
-                                std::vector<Handles> all(world);
-                                CUX(cudaMemcpyAsync(all.data(), dh, sizeof(Handles) * world, cudaMemcpyDeviceToHost, c->stream));
-                                CUX(cudaStreamSynchronize(c->stream));
-                                cudaFree(dh);
-                                ok = ok && r3 == ncclSuccess;
-                                c->peer_tmp.assign(world, nullptr); c->peer_av.assign(world, nullptr);
-                                c->peer_tmp[c->rank] = c->tmp; c->peer_av[c->rank] = c->Av_full;
-                                for (int r = 0; r < world && ok; r++) {
-                                        if (r == c->rank) continue;
-                                        void *a = nullptr, *b = nullptr;
-                                        ok = cudaIpcOpenMemHandle(&a, all[r].tmp, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess &&
-                                             cudaIpcOpenMemHandle(&b, all[r].av, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
-                                        c->peer_tmp[r] = (u32 *)a; c->peer_av[r] = (u32 *)b;
-                                }
-                                cudaGetLastError();            // a failed open must not poison later calls
-                                // every rank must take the same path: agree through a sum
-                                unsigned long long *flag = nullptr, hflag = ok ? 1ull : 0ull;
-                                CUX(cudaMalloc(&flag, sizeof(unsigned long long)));
-                                CUX(cudaMemcpyAsync(flag, &hflag, sizeof(hflag), cudaMemcpyHostToDevice, c->stream));
-                                NC(g_nccl.AllReduce(flag, flag, 1, ncclUint64, ncclSum, c->comm, c->stream));
-                                CUX(cudaMemcpyAsync(&hflag, flag, sizeof(hflag), cudaMemcpyDeviceToHost, c->stream));
-                                CUX(cudaStreamSynchronize(c->stream));
-                                cudaFree(flag);
-                                c->p2p = hflag == (unsigned long long)world;
-                                if (c->p2p) {
-                                        c->copy_streams.resize(world - 1); c->ev_copies.resize(world - 1);
-                                        for (auto &st : c->copy_streams) CUX(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-                                        for (auto &ev : c->ev_copies) CUX(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-                                        CUX(cudaMalloc(&c->barrier_word, sizeof(u64)));
-                                        CUX(cudaMemsetAsync(c->barrier_word, 0, sizeof(u64), c->stream));
-                                        CUX(cudaStreamSynchronize(c->stream));
-                                }
-                        }
-                }
-                if (grid_req) {
-                        int rc = grid_create(c, gridP, gridQ, prm->chunk_len, nnz, idxN, idxM, dx, grid_cntN, grid_cntM);
-                        free_coo();
-                        if (rc) { blk_destroy(c); return 1; }
-                }
-        }
-#undef CUX
-        *out = c;
-        return 0;
-}
 
 int blk_set_state(blk_ctx *c, const uint32_t *v, const uint32_t *p, int32_t n_iterations)
 {
         if (!c || !v) return fail("blk_set_state: null argument");
+        if (c->is_group()) return group_run(c, [&](blk_ctx *mem, int) { return blk_set_state(mem, v, p, n_iterations); });
         CU(cudaSetDevice(c->device));
         const int np = c->geo.np, n = c->geo.n;
-        if (upload_rows(c, c->v, v, c->N, c->n_new2old)) return 1;
-        int64_t ln = c->n1() - c->n0();
+        // Every rank reads only ITS rows of the host blocks (1/world of the PCIe traffic); the rest of v arrives
+        // from the peers over NVLink.  (The relabelling map exists only when world == 1: all rows are local.)
+        const int64_t n0 = c->n0(), ln = c->n1() - n0;
+        if (upload_rows(c, c->n_old2new ? c->v : c->v + (size_t)n0 * np, v + (size_t)n0 * n, ln, c->n_old2new, n0)) return 1;
+        if (c->world > 1 && allgather_rows(c, c->v, c->n_off)) return 1;
         if (p) {
-                // (maps exist only when world == 1, where the local block is the whole dimension)
-                if (upload_rows(c, c->p, p + (size_t)c->n0() * n, ln, c->n_new2old)) return 1;
+                if (upload_rows(c, c->p, p + (size_t)n0 * n, ln, c->n_old2new, n0)) return 1;
         } else {
                 CU(cudaMemsetAsync(c->p, 0, sizeof(u32) * (size_t)(ln > 0 ? ln : 1) * np, c->stream));
         }
@@ -1656,8 +1942,9 @@ int blk_set_state(blk_ctx *c, const uint32_t *v, const uint32_t *p, int32_t n_it
                 // invariant of the multi-GPU loop: tmp = S1 v (gathered), Tp = S1 p (local rows)
                 u32 *pfull = nullptr;
                 if (p) {
-                        CU(cudaMalloc(&pfull, sizeof(u32) * (size_t)c->N * np));
-                        if (upload_rows(c, pfull, p, c->N)) { cudaFree(pfull); return 1; }
+                        CU(cudaMalloc(&pfull, sizeof(u32) * (size_t)gather_cap(c->n_off) * np));
+                        cudaError_t e = cudaMemcpyAsync(pfull + (size_t)n0 * np, c->p, sizeof(u32) * (size_t)ln * np, cudaMemcpyDeviceToDevice, c->stream);
+                        if (e != cudaSuccess || allgather_rows(c, pfull, c->n_off)) { cudaFree(pfull); return e != cudaSuccess ? fail(cudaGetErrorString(e)) : 1; }
                 }
                 int rc = mg_prepare(c, pfull);
                 cudaFree(pfull);
@@ -1670,6 +1957,8 @@ int blk_set_state(blk_ctx *c, const uint32_t *v, const uint32_t *p, int32_t n_it
         memset(c->h_state, 0, sizeof(DevSmall));
         c->h_state->iters = n_iterations;
         c->h_state->halt = 1;
+        c->h_state->check = c->check ? 1 : 0;
+        c->h_state->fault_iter = c->check_fault;
         if (push_state(c)) return 1;
         CU(cudaStreamSynchronize(c->stream));
         return 0;
@@ -1678,6 +1967,14 @@ int blk_set_state(blk_ctx *c, const uint32_t *v, const uint32_t *p, int32_t n_it
 int blk_iterate(blk_ctx *c, int32_t max_iters, int32_t *iters_total, int32_t *stopped)
 {
         if (!c) return fail("blk_iterate: null context");
+        if (c->is_group()) {
+                std::vector<int32_t> it(c->members.size(), 0), st(c->members.size(), 0);
+                if (group_run(c, [&](blk_ctx *mem, int r) { return blk_iterate(mem, max_iters, &it[(size_t)r], &st[(size_t)r]); })) return 1;
+                c->iters = it[0]; c->stopped = st[0];
+                if (iters_total) *iters_total = it[0];
+                if (stopped) *stopped = st[0];
+                return 0;
+        }
         CU(cudaSetDevice(c->device));
         if (max_iters > 0 && !c->stopped) {
                 c->h_state->iters = c->iters;
@@ -1711,6 +2008,16 @@ int blk_iterate(blk_ctx *c, int32_t max_iters, int32_t *iters_total, int32_t *st
                         if (c->profiling) tm.resolve(c);
                         if (c->h_state->halt) break;
                 }
+                if (c->h_state->check_failed) {
+                        // the reference aborts on a failed assert of correctness_tests (sequential/lanczos_modp.c:532-557, :647)
+                        static const char *what[5] = {"vtAv not symmetric", "vtAAv not symmetric", "winv not symmetric",
+                                                      "winv not supported on the pivots", "winv * vtAv * D != D"};
+                        std::string msg = "correctness_tests failed in iteration " + std::to_string(c->h_state->iters + 1) + ":";
+                        for (int b = 0; b < 5; b++)
+                                if (c->h_state->check_failed & (1 << b)) msg += std::string(" ") + what[b] + ";";
+                        c->iters = c->h_state->iters;
+                        return fail(msg);
+                }
                 int before = c->iters;
                 c->iters = c->h_state->iters;
                 c->stopped = c->h_state->stopped;
@@ -1724,85 +2031,126 @@ int blk_iterate(blk_ctx *c, int32_t max_iters, int32_t *iters_total, int32_t *st
         return 0;
 }
 
+// What one rank contributes to blk_get_state: rows of v / Av / p straight into the caller's blocks (host layout,
+// n per row, written at their global row position) and rows of the device's tmp into `ht` (Mc x n).
+// whole = false: only this rank's rows (the blocks of a job are then assembled from the ranks' slices: group
+// contexts, blk_get_state_local); whole = true: every row -- at world > 1 the missing rows are fetched from the
+// peers over NVLink first, because a rank of a multi-process job must return complete blocks.
+static int download_state(blk_ctx *c, u32 *v, u32 *Av, u32 *p, u32 *ht, bool whole)
+{
+        CU(cudaSetDevice(c->device));
+        const int n = c->geo.n, np = c->geo.np;
+        if (c->grid_on && grid_export(c)) return 1;
+        const bool all = whole && c->world > 1;
+        const int64_t n0 = c->n0(), ln = c->n1() - c->n0(), m0 = c->m0(), lm = c->m1() - c->m0();
+        if (v) {
+                if (all) {
+                        if (allgather_rows(c, c->v, c->n_off)) return 1;
+                        if (download_rows(c, v, c->v, c->N)) return 1;
+                } else if (download_rows(c, v + (size_t)n0 * n, c->n_old2new ? c->v : c->v + (size_t)n0 * np, ln, c->n_old2new, n0)) return 1;
+        }
+        for (int which = 0; which < 2; which++) {
+                u32 *dst = which ? p : Av;
+                if (!dst) continue;
+                const u32 *src = which ? c->p : c->Av;                 // local rows
+                if (all) {
+                        u32 *full = nullptr;
+                        CU(cudaMalloc(&full, sizeof(u32) * (size_t)gather_cap(c->n_off) * np));
+                        int rc = 0;
+                        if (cudaMemcpyAsync(full + (size_t)n0 * np, src, sizeof(u32) * (size_t)ln * np, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess)
+                                rc = fail("blk_get_state: device copy failed");
+                        if (!rc) rc = allgather_rows(c, full, c->n_off);
+                        if (!rc) rc = download_rows(c, dst, full, c->N);
+                        cudaFree(full);
+                        if (rc) return 1;
+                } else if (download_rows(c, dst + (size_t)n0 * n, src, ln, c->n_old2new, n0)) return 1;
+        }
+        if (ht) {
+                if (c->mg_recur && !c->ran_since_set) {
+                        // nothing has run since blk_set_state: the reference's tmp is still all zero there (the
+                        // device already holds S1*v for the first iteration); the caller zero-fills
+                } else if (c->mg_recur && !c->tmp_is_spmv && c->Mc > c->N) {
+                        // the device tmp already belongs to the NEXT iteration; the reference still shows the
+                        // previous product in rows [N,Mc): the saved copy
+                        if (all) {
+                                u32 *full = nullptr;
+                                CU(cudaMalloc(&full, sizeof(u32) * (size_t)gather_cap(c->m_off) * np));
+                                int rc = 0;
+                                if (cudaMemcpyAsync(full + (size_t)m0 * np, c->tmp_prev, sizeof(u32) * (size_t)lm * np, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess)
+                                        rc = fail("blk_get_state: device copy failed");
+                                if (!rc) rc = allgather_rows(c, full, c->m_off);
+                                if (!rc) rc = download_rows(c, ht, full, c->Mc);
+                                cudaFree(full);
+                                if (rc) return 1;
+                        } else if (download_rows(c, ht + (size_t)m0 * n, c->tmp_prev, lm)) return 1;
+                } else if (all || c->world == 1) {
+                        if (download_rows(c, ht, c->tmp, c->Mc)) return 1;
+                } else if (download_rows(c, ht + (size_t)m0 * n, c->tmp + (size_t)m0 * np, lm)) return 1;
+        }
+        return 0;
+}
+
+// The reference's tmp block from the device's (DESIGN.md "tmp"): the reference's tmp holds the next v in rows
+// [0,N) after orthogonalize + copy (:652-656) and S1*v in rows [0,Mc) after the first product (:635).
+static void compose_tmp(const blk_ctx *c, u32 *tmp, std::vector<u32> &ht, const u32 *vsrc, int64_t pad)
+{
+        const int n = c->geo.n;
+        const int64_t N = c->N, Mc = c->Mc;
+        memset(tmp, 0, sizeof(u32) * (size_t)pad);
+        if (c->mg_recur && !c->ran_since_set) std::fill(ht.begin(), ht.end(), 0u);
+        if (c->tmp_is_spmv) {
+                if (c->any_ortho && N > Mc)
+                        memcpy(tmp + (size_t)Mc * n, vsrc + (size_t)Mc * n, sizeof(u32) * (size_t)(N - Mc) * n);
+                memcpy(tmp, ht.data(), sizeof(u32) * (size_t)Mc * n);
+        } else {
+                if (Mc > N)
+                        memcpy(tmp + (size_t)N * n, ht.data() + (size_t)N * n, sizeof(u32) * (size_t)(Mc - N) * n);
+                if (c->any_ortho) memcpy(tmp, vsrc, sizeof(u32) * (size_t)N * n);
+                else memcpy(tmp, ht.data(), sizeof(u32) * (size_t)std::min(N, Mc) * n);
+        }
+}
+
 int blk_get_state(blk_ctx *c, uint32_t *v, uint32_t *tmp, uint32_t *Av, uint32_t *p)
 {
         if (!c) return fail("blk_get_state: null context");
-        CU(cudaSetDevice(c->device));
-        const int n = c->geo.n, np = c->geo.np;
+        const int n = c->geo.n;
         const int64_t pad = blk_block_pad(c->nrows, c->ncols, n, c->right);
         const int64_t N = c->N, Mc = c->Mc;
-        if (c->grid_on && grid_export(c)) return 1;
-        // v is complete on every rank only right after an all-gather; refresh it
-        if (c->world > 1 && allgather_rows(c, c->v, c->n_off)) return 1;
-        std::vector<u32> hv;
-        const u32 *vsrc = nullptr;
-        if (v) {
-                // straight into the caller's buffer (fast when it is pinned)
-                if (download_rows(c, v, c->v, N, c->n_old2new)) return 1;
-                memset(v + (size_t)N * n, 0, sizeof(u32) * (size_t)(pad - N * n));
-                vsrc = v;
-        } else if (tmp) {
-                hv.resize((size_t)N * n);
-                if (download_rows(c, hv.data(), c->v, N, c->n_old2new)) return 1;
-                vsrc = hv.data();
-        }
-        if (tmp) {
-                // see DESIGN.md "tmp": the reference's tmp holds the next v in rows [0,N) after
-                // orthogonalize + copy (:652-656) and S1*v in rows [0,Mc) after the first product (:635)
-                memset(tmp, 0, sizeof(u32) * (size_t)pad);
-                std::vector<u32> ht((size_t)Mc * n);
-                if (c->mg_recur && !c->ran_since_set) {
-                        // nothing has run since blk_set_state: the reference's tmp is still all zero there
-                        // (the device already holds S1*v for the first iteration)
-                        std::fill(ht.begin(), ht.end(), 0u);
-                } else if (c->mg_recur && !c->tmp_is_spmv && Mc > N) {
-                        // the device tmp already belongs to the NEXT iteration; the reference still shows
-                        // the previous product in rows [N,Mc): gather the saved copy
-                        u32 *full = nullptr;
-                        CU(cudaMalloc(&full, sizeof(u32) * (size_t)gather_cap(c->m_off) * np));
-                        CU(cudaMemcpyAsync(full + (size_t)c->m0() * np, c->tmp_prev, sizeof(u32) * (size_t)(c->m1() - c->m0()) * np,
-                                           cudaMemcpyDeviceToDevice, c->stream));
-                        if (allgather_rows(c, full, c->m_off)) { cudaFree(full); return 1; }
-                        int rc = download_rows(c, ht.data(), full, Mc);
-                        cudaFree(full);
-                        if (rc) return 1;
-                } else if (download_rows(c, ht.data(), c->tmp, Mc)) return 1;
-                if (c->tmp_is_spmv) {
-                        if (c->any_ortho && N > Mc)
-                                memcpy(tmp + (size_t)Mc * n, vsrc + (size_t)Mc * n, sizeof(u32) * (size_t)(N - Mc) * n);
-                        memcpy(tmp, ht.data(), sizeof(u32) * (size_t)Mc * n);
-                } else {
-                        if (Mc > N)
-                                memcpy(tmp + (size_t)N * n, ht.data() + (size_t)N * n, sizeof(u32) * (size_t)(Mc - N) * n);
-                        if (c->any_ortho) memcpy(tmp, vsrc, sizeof(u32) * (size_t)N * n);
-                        else memcpy(tmp, ht.data(), sizeof(u32) * (size_t)std::min(N, Mc) * n);
-                }
-        }
-        for (int which = 0; which < 2; which++) {
-                uint32_t *dst = which ? p : Av;
-                if (!dst) continue;
-                memset(dst, 0, sizeof(u32) * (size_t)pad);
-                u32 *src = which ? c->p : c->Av;
-                if (c->world == 1) {
-                        if (download_rows(c, dst, src, N, c->n_old2new)) return 1;
-                } else {
-                        u32 *full = nullptr;
-                        CU(cudaMalloc(&full, sizeof(u32) * (size_t)gather_cap(c->n_off) * np));
-                        int64_t ln = c->n1() - c->n0();
-                        CU(cudaMemcpyAsync(full + (size_t)c->n0() * np, src, sizeof(u32) * (size_t)ln * np,
-                                           cudaMemcpyDeviceToDevice, c->stream));
-                        if (allgather_rows(c, full, c->n_off)) { cudaFree(full); return 1; }
-                        int rc = download_rows(c, dst, full, N);
-                        cudaFree(full);
-                        if (rc) return 1;
-                }
-        }
+        std::vector<u32> hv, ht;
+        u32 *vdst = v;
+        if (!v && tmp) { hv.resize((size_t)N * n); vdst = hv.data(); }
+        if (tmp) ht.resize((size_t)Mc * n);
+        u32 *htp = tmp ? ht.data() : nullptr;
+        const blk_ctx *flags = c;
+        if (c->is_group()) {
+                // one host block, every GPU writes its own rows into it: PCIe traffic is shared, nothing crosses NVLink
+                if (group_run(c, [&](blk_ctx *mem, int) { return download_state(mem, vdst, Av, p, htp, false); })) return 1;
+                flags = c->members[0];
+        } else if (download_state(c, vdst, Av, p, htp, true)) return 1;
+        const size_t tail = sizeof(u32) * (size_t)(pad - N * n);
+        if (v) memset(v + (size_t)N * n, 0, tail);
+        if (Av) memset(Av + (size_t)N * n, 0, tail);
+        if (p) memset(p + (size_t)N * n, 0, tail);
+        if (tmp) compose_tmp(flags, tmp, ht, vdst, pad);
         return 0;
+}
+
+int blk_get_state_local(blk_ctx *c, uint32_t *v, uint32_t *Av, uint32_t *p)
+{
+        if (!c) return fail("blk_get_state_local: null context");
+        if (c->is_group()) return blk_get_state(c, v, nullptr, Av, p);
+        return download_state(c, v, Av, p, nullptr, false);
 }
 
 int blk_final_check(blk_ctx *c, int32_t *v_nonzero, int32_t *vtm_zero)
 {
         if (!c || !v_nonzero || !vtm_zero) return fail("blk_final_check: null argument");
+        if (c->is_group()) {
+                std::vector<int32_t> a(c->members.size(), 0), b(c->members.size(), 0);
+                if (group_run(c, [&](blk_ctx *mem, int r) { return blk_final_check(mem, &a[(size_t)r], &b[(size_t)r]); })) return 1;
+                *v_nonzero = a[0]; *vtm_zero = b[0];
+                return 0;
+        }
         CU(cudaSetDevice(c->device));
         const int np = c->geo.np;
         int nz = 0, big = 0;
@@ -1832,13 +2180,19 @@ int blk_final_check(blk_ctx *c, int32_t *v_nonzero, int32_t *vtm_zero)
 int blk_check_kernel_block(blk_ctx *c, const uint32_t *x, int32_t *ok)
 {
         if (!c || !x || !ok) return fail("blk_check_kernel_block: null argument");
+        if (c->is_group()) {
+                std::vector<int32_t> o(c->members.size(), 0);
+                if (group_run(c, [&](blk_ctx *mem, int r) { return blk_check_kernel_block(mem, x, &o[(size_t)r]); })) return 1;
+                *ok = o[0];
+                return 0;
+        }
         CU(cudaSetDevice(c->device));
         const int np = c->geo.np;
         const int64_t lm = c->m1() - c->m0();
         u32 *dx = nullptr, *dy = nullptr;
         CU(cudaMalloc(&dx, sizeof(u32) * (size_t)c->N * np));
         CU(cudaMalloc(&dy, sizeof(u32) * (size_t)(lm > 0 ? lm : 1) * np));
-        int rc = upload_rows(c, dx, x, c->N, c->n_new2old);
+        int rc = upload_rows(c, dx, x, c->N, c->n_old2new);
         int nz = 0, big = 0, ynz = 0, ybig = 0;
         if (!rc) rc = scan_rows(c, dx + (size_t)c->n0() * np, c->n1() - c->n0(), &nz, &big);
         if (!rc && !big) {
@@ -1855,6 +2209,7 @@ int blk_check_kernel_block(blk_ctx *c, const uint32_t *x, int32_t *ok)
 int blk_get_small(blk_ctx *c, uint32_t *vtAv, uint32_t *vtAAv, uint32_t *winv, uint32_t *d, int32_t *npiv)
 {
         if (!c) return fail("blk_get_small: null context");
+        if (c->is_group()) return blk_get_small(c->members[0], vtAv, vtAAv, winv, d, npiv);
         CU(cudaSetDevice(c->device));
         const int n = c->geo.n, np = c->geo.np;
         std::vector<u32> h((size_t)MAT_COUNT * np * np);
@@ -1883,6 +2238,15 @@ static SpOp *op_for(blk_ctx *c, int transpose, bool *is_s1)
 int blk_spmv(blk_ctx *c, uint32_t *y, const uint32_t *x, int32_t transpose)
 {
         if (!c || !y || !x) return fail("blk_spmv: null argument");
+        if (c->is_group()) {
+                // every member returns the whole product (gathered over NVLink); only the first one's goes to y
+                const size_t out = (size_t)((transpose != 0) == (c->right == 0) ? c->Mc : c->N) * c->geo.n;
+                return group_run(c, [&](blk_ctx *mem, int r) {
+                        if (r == 0) return blk_spmv(mem, y, x, transpose);
+                        std::vector<u32> scratch(out);
+                        return blk_spmv(mem, scratch.data(), x, transpose);
+                });
+        }
         CU(cudaSetDevice(c->device));
         const int np = c->geo.np;
         bool s1;
@@ -1892,7 +2256,7 @@ int blk_spmv(blk_ctx *c, uint32_t *y, const uint32_t *x, int32_t transpose)
         u32 *dx = nullptr, *dy = nullptr;
         CU(cudaMalloc(&dx, sizeof(u32) * (size_t)in_rows * np));
         CU(cudaMalloc(&dy, sizeof(u32) * (size_t)gather_cap(off) * np));
-        int rc = upload_rows(c, dx, x, in_rows, s1 ? c->n_new2old : nullptr);
+        int rc = upload_rows(c, dx, x, in_rows, s1 ? c->n_old2new : nullptr);
         if (!rc) {
                 // poison the output: every row must be written by the kernels
                 cudaMemsetAsync(dy, 0xff, sizeof(u32) * (size_t)out_rows * np, c->stream);
@@ -1911,6 +2275,7 @@ int blk_block_dot_products(blk_ctx *c, uint32_t *vtAv, uint32_t *vtAAv, int64_t 
                            const uint32_t *v)
 {
         if (!c || !vtAv || !vtAAv || !Av || !v || N < 0) return fail("blk_block_dot_products: bad argument");
+        if (c->is_group()) return blk_block_dot_products(c->members[0], vtAv, vtAAv, N, Av, v);
         CU(cudaSetDevice(c->device));
         const int np = c->geo.np, n = c->geo.n;
         u32 *dv = nullptr, *da = nullptr, *mats = nullptr;
@@ -1950,6 +2315,7 @@ static void put_small(std::vector<u32> &h, int which, const uint32_t *src, int n
 int blk_semi_inverse(blk_ctx *c, const uint32_t *M_, uint32_t *winv, uint32_t *d, int32_t *npiv)
 {
         if (!c || !M_ || !winv || !d) return fail("blk_semi_inverse: null argument");
+        if (c->is_group()) return blk_semi_inverse(c->members[0], M_, winv, d, npiv);
         CU(cudaSetDevice(c->device));
         const int np = c->geo.np, n = c->geo.n;
         std::vector<u32> h((size_t)MAT_COUNT * np * np, 0);
@@ -1979,6 +2345,7 @@ int blk_orthogonalize(blk_ctx *c, const uint32_t *v, uint32_t *tmp, uint32_t *p,
 {
         if (!c || !v || !tmp || !p || !d || !vtAv || !vtAAv || !winv || !Av || N < 0)
                 return fail("blk_orthogonalize: bad argument");
+        if (c->is_group()) return blk_orthogonalize(c->members[0], v, tmp, p, d, vtAv, vtAAv, winv, N, Av);
         CU(cudaSetDevice(c->device));
         const int np = c->geo.np, n = c->geo.n;
         std::vector<u32> h((size_t)MAT_COUNT * np * np, 0);
@@ -2010,6 +2377,10 @@ int blk_orthogonalize(blk_ctx *c, const uint32_t *v, uint32_t *tmp, uint32_t *p,
 int blk_set_profiling(blk_ctx *c, int32_t on)
 {
         if (!c) return fail("null context");
+        if (c->is_group()) {
+                for (blk_ctx *mem : c->members) blk_set_profiling(mem, on);
+                return 0;
+        }
         c->profiling = on != 0;
         for (int i = 0; i < BLK_PH_COUNT; i++) { c->ph_ms[i] = 0; c->ph_launch[i] = 0; }
         return 0;
@@ -2018,6 +2389,7 @@ int blk_set_profiling(blk_ctx *c, int32_t on)
 int blk_get_phase_times(blk_ctx *c, double ms[BLK_PH_COUNT], int64_t launches[BLK_PH_COUNT])
 {
         if (!c) return fail("null context");
+        if (c->is_group()) return blk_get_phase_times(c->members[0], ms, launches);
         for (int i = 0; i < BLK_PH_COUNT; i++) {
                 if (ms) ms[i] = c->ph_ms[i];
                 if (launches) launches[i] = c->ph_launch[i];
@@ -2028,6 +2400,12 @@ int blk_get_phase_times(blk_ctx *c, double ms[BLK_PH_COUNT], int64_t launches[BL
 int blk_time_spmv(blk_ctx *c, int32_t transpose, int32_t reps, double *ms_avg)
 {
         if (!c || reps < 1 || !ms_avg) return fail("blk_time_spmv: bad argument");
+        if (c->is_group()) {
+                std::vector<double> ms(c->members.size(), 0.0);
+                if (group_run(c, [&](blk_ctx *mem, int r) { return blk_time_spmv(mem, transpose, reps, &ms[(size_t)r]); })) return 1;
+                *ms_avg = *std::max_element(ms.begin(), ms.end());        // the slowest shard is the product's time
+                return 0;
+        }
         CU(cudaSetDevice(c->device));
         const int np = c->geo.np;
         bool s1;
@@ -2053,11 +2431,32 @@ int blk_time_spmv(blk_ctx *c, int32_t transpose, int32_t reps, double *ms_avg)
         return 0;
 }
 
-int64_t blk_kernel_launches(blk_ctx *c) { return c ? c->launches : 0; }
+int64_t blk_kernel_launches(blk_ctx *c)
+{
+        if (!c) return 0;
+        int64_t total = c->launches;
+        for (blk_ctx *mem : c->members) total += mem->launches;
+        return total;
+}
 
 int blk_get_info(blk_ctx *c, blk_info *info)
 {
         if (!c || !info) return fail("blk_get_info: null argument");
+        if (c->is_group()) {
+                // the job as a whole: every row is local, sizes summed over the members
+                if (blk_get_info(c->members[0], info)) return 1;
+                for (size_t r = 1; r < c->members.size(); r++) {
+                        blk_info one;
+                        if (blk_get_info(c->members[r], &one)) return 1;
+                        for (int i = 0; i < 2; i++) {
+                                info->nnz_local[i] += one.nnz_local[i]; info->stored_local[i] += one.stored_local[i];
+                                info->tiles[i] += one.tiles[i];
+                        }
+                        info->device_bytes += one.device_bytes;
+                }
+                info->local_N0 = 0; info->local_N1 = c->N; info->local_M0 = 0; info->local_M1 = c->Mc;
+                return 0;
+        }
         memset(info, 0, sizeof(*info));
         info->N = c->N; info->Mc = c->Mc;
         info->local_N0 = c->n0(); info->local_N1 = c->n1();

@@ -249,24 +249,27 @@ k_ortho(int64_t rows, const u32 *v, const u32 *__restrict__ Av, const u32 *p, u3
         }
 }
 
+// host-layout rows (n per row) -> device rows (np per row, zero padded).  Row r of src goes to device row
+// map[r0 + r] when a relabelling is in force (scatter: src is read in order), else to row r of dst.
 __global__ void k_pad_rows(const u32 *__restrict__ src, u32 *__restrict__ dst, int64_t rows, int n, int np,
-                           const u32 *__restrict__ map)
+                           const u32 *__restrict__ map, int64_t r0)
 {
         int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
         if (e >= rows * np) return;
         int64_t r = e / np;
         int j = (int)(e - r * np);
-        int64_t sr = map ? map[r] : r;
-        dst[e] = j < n ? src[sr * n + j] : 0u;
+        int64_t dr = map ? (int64_t)map[r0 + r] : r;
+        dst[dr * np + j] = j < n ? src[r * n + j] : 0u;
 }
+// device rows -> host-layout rows: row r of dst comes from device row map[r0 + r] (gather), else row r of src
 __global__ void k_unpad_rows(const u32 *__restrict__ src, u32 *__restrict__ dst, int64_t rows, int n, int np,
-                             const u32 *__restrict__ map)
+                             const u32 *__restrict__ map, int64_t r0)
 {
         int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
         if (e >= rows * n) return;
         int64_t r = e / n;
         int j = (int)(e - r * n);
-        int64_t sr = map ? map[r] : r;
+        int64_t sr = map ? (int64_t)map[r0 + r] : r;
         dst[e] = src[sr * np + j];
 }
 
@@ -319,13 +322,14 @@ int dots_num_blocks(int64_t rows, int np)
         int teams = DOTS_TB / team;
         int64_t want = (rows + (int64_t)teams * 4 - 1) / ((int64_t)teams * 4);     // >= 4 rows per team
         if (want < 1) want = 1;
-        if (want > 148 * 4) want = 148 * 4;
+        if (want > blk_sm_count() * 4) want = blk_sm_count() * 4;
         return (int)want;
 }
 
 int launch_dots(const Geometry &geo, const ModP &m, int64_t rows, const u32 *v, const u32 *Av,
                 u64 *sums, int nblocks, const DevSmall *state, const SmallFuse &fuse, cudaStream_t st)
 {
+        if (rows <= 0 && !fuse.counter) return 0;       // an empty shard adds nothing to the sums
         if (dense_umma_supported(geo.np, rows)) {
                 int k = launch_dots_umma(geo.np, m, rows, v, Av, sums, state, fuse, st);
                 if (k > 0) return k;          // (a tensor map that cannot be encoded falls through to mma.sync)
@@ -354,7 +358,8 @@ int launch_small(const Geometry &geo, const ModP &m, u64 *sums, u32 *mats, DevSm
 int launch_ortho(const Geometry &geo, const ModP &m, int64_t rows, u32 *v, const u32 *Av, u32 *p,
                  u32 *v_out, u32 *p_out, const u32 *mats, const DevSmall *state, int force, cudaStream_t st)
 {
-        if (rows > 0 && dense_umma_supported(geo.np, rows)) {
+        if (rows <= 0) return 0;
+        if (dense_umma_supported(geo.np, rows)) {
                 int k = launch_ortho_umma(geo.np, m, rows, v, Av, p, v_out, p_out, mats, state, force, st);
                 if (k > 0) return k;
         }
@@ -380,17 +385,17 @@ void dense_prepare(const Geometry &geo, const ModP &m)
         dense_umma_prepare(geo.np);
 }
 
-int launch_pad_rows(const u32 *src, u32 *dst, int64_t rows, int n, int np, const u32 *map, cudaStream_t st)
+int launch_pad_rows(const u32 *src, u32 *dst, int64_t rows, int n, int np, const u32 *map, int64_t r0, cudaStream_t st)
 {
         int64_t tot = rows * np;
         if (tot == 0) return 0;
-        k_pad_rows<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(src, dst, rows, n, np, map);
+        k_pad_rows<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(src, dst, rows, n, np, map, r0);
         return 1;
 }
-int launch_unpad_rows(const u32 *src, u32 *dst, int64_t rows, int n, int np, const u32 *map, cudaStream_t st)
+int launch_unpad_rows(const u32 *src, u32 *dst, int64_t rows, int n, int np, const u32 *map, int64_t r0, cudaStream_t st)
 {
         int64_t tot = rows * n;
         if (tot == 0) return 0;
-        k_unpad_rows<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(src, dst, rows, n, np, map);
+        k_unpad_rows<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(src, dst, rows, n, np, map, r0);
         return 1;
 }

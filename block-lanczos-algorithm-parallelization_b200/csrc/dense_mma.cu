@@ -328,7 +328,7 @@ int ortho_go(int64_t rows, u32 *v, const u32 *Av, u32 *p, u32 *v_out, u32 *p_out
         }
         int64_t tiles = (rows + 15) / 16;
         int64_t blocks = (tiles + 3) / 4;
-        int64_t cap = 148 * (NP == 32 ? 4 : 8);
+        int64_t cap = (int64_t)blk_sm_count() * (NP == 32 ? 4 : 8);
         if (blocks > cap) blocks = cap;
         if (blocks < 1) blocks = 1;
         k_ortho_mma<NP><<<(unsigned)blocks, 128, ortho_smem<NP>(), st>>>(rows, v, Av, p, v_out, p_out, mats, m, state, force);
@@ -342,7 +342,7 @@ int dots_go(int64_t rows, const u32 *v, const u32 *Av, u64 *sums, const ModP &m,
         constexpr int NB = NP / (NP < 16 ? NP : 16);
         int64_t steps = (rows + 31) / 32;
         int64_t bx = (steps + 7) / 8;                    // >= 8 steps per block
-        int64_t cap = 148 * 8 / (NB * NB);
+        int64_t cap = (int64_t)blk_sm_count() * 8 / (NB * NB);
         if (bx > cap) bx = cap;
         if (bx < 1) bx = 1;
         dim3 grid((unsigned)bx, NB * NB);

@@ -582,7 +582,7 @@ int launch_dots_umma(int np, const ModP &m, int64_t rows, const u32 *v, const u3
         CUtensorMap mv, ma;
         if (!row_map(&mv, v, rows) || !row_map(&ma, Av, rows)) return -1;
         const int64_t ntile = (rows + TILE_ROWS - 1) / TILE_ROWS;
-        const unsigned grid = (unsigned)(ntile < 148 ? ntile : 148);
+        const unsigned grid = (unsigned)(ntile < blk_sm_count() ? ntile : blk_sm_count());
         if (wide < 0) wide = umma_mode() == 2;
         if (wide)
                 k_dots_umma<true><<<grid, THREADS, DOTS_SMEM, st>>>(mv, ma, ntile, (unsigned long long *)sums, m, state, fuse);
@@ -602,7 +602,7 @@ int launch_ortho_umma(int np, const ModP &m, int64_t rows, u32 *v, const u32 *Av
             !row_map(&mvo, v_out, rows, OT_ROWS) || !row_map(&mpo, p_out, rows, OT_ROWS))
                 return -1;
         const int64_t ntile = (rows + OT_ROWS - 1) / OT_ROWS;
-        const unsigned grid = (unsigned)(ntile < 148 ? ntile : 148);
+        const unsigned grid = (unsigned)(ntile < blk_sm_count() ? ntile : blk_sm_count());
         if (variant < 0) variant = ORTHO_DEFAULT_VARIANT;
         switch (variant) {
         case 0: k_ortho_umma<64, 5><<<grid, 11 * 32, ortho_smem(5), st>>>(mv, ma, mp, mvo, mpo, ntile, mats, m, state, force); break;

@@ -138,9 +138,9 @@ static int pick_chunk_len(int64_t stored, int G)
         // chain more than 64 products (modp.cuh)
         // (config 4, n = 16: Q = 64 14.57 it/s, 32 14.42, 16 13.94 -- longer chunks mean fewer tile
         // borders to stitch; small operators need short chunks to fill the SMs)
-        if (stored / ((int64_t)G * 64) >= 148 * 32) return 64;
+        if (stored / ((int64_t)G * 64) >= (int64_t)blk_sm_count() * 32) return 64;
         int Q = 32;
-        while (Q > 8 && stored / ((int64_t)G * Q) < 148 * 8) Q >>= 1;
+        while (Q > 8 && stored / ((int64_t)G * Q) < (int64_t)blk_sm_count() * 8) Q >>= 1;
         return Q;
 }
 
@@ -154,6 +154,13 @@ std::string build_operator(SpOp *op, const Geometry &geo, int chunk_len, int64_t
         if (rows >= (1ll << 31) || cols >= (1ll << 31)) return "matrix dimension >= 2^31";
         if (chunk_len != 0 && (chunk_len < 8 || chunk_len > 64 || (chunk_len & (chunk_len - 1))))
                 return "chunk_len must be a power of two in [8,64]";
+        if (rows == 0) {
+                // an empty shard (more ranks than rows): no tiles, one empty piece; launch_spmv skips it
+                if (nnz != 0) return "entries given for an operator without rows";
+                op->Q = chunk_len ? chunk_len : 8;
+                op->piece_tile.assign({0, 0}); op->piece_row.assign({0, 0}); op->piece_scan.assign({0, 0});
+                return "";
+        }
 
         u32 *cnt = nullptr, *empty = nullptr, *vals[2] = {nullptr, nullptr};
         u64 *keys[2] = {nullptr, nullptr}, *rowptr = nullptr;

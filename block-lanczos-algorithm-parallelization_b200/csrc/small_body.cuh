@@ -163,6 +163,39 @@ static __device__ __noinline__ void small_body(int n, int np, unsigned long long
                 npiv = 1;
         }
 
+        // ---- correctness_tests (sequential/lanczos_modp.c:532-557), on request (BLK_CHECK=1): vtAv, vtAAv, winv
+        // symmetric; winv supported on the pivot rows/columns; winv * (vtAv D) == D.  The reference asserts them
+        // on every iteration; here a violation halts the loop before anything is updated and blk_iterate fails.
+        if (mode == 0 && state->check) {
+                __shared__ int s_bad;
+                if (tid == 0) {
+                        s_bad = 0;
+                        if (state->fault_iter > 0 && state->iters + 1 == state->fault_iter) A[n > 1 ? 1 : 0] ^= 1u;   // fault injection
+                }
+                __syncthreads();
+                int bad = 0;
+                for (int e = tid; e < nn; e += SMALL_TB) {
+                        const int i = e / n, j = e - i * n;
+                        if (A[e] != A[j * n + i]) bad |= 1;
+                        if (B[e] != B[j * n + i]) bad |= 2;
+                        if (W[e] != W[j * n + i]) bad |= 4;
+                        if (W[e] != 0 && !d[i] && !d[j]) bad |= 8;
+                        u64 s = 0;
+                        if (d[j])
+                                for (int k = 0; k < n; k++) {
+                                        s += (u64)W[i * n + k] * A[k * n + j];
+                                        mp_fold(s, m);
+                                }
+                        if (mp_reduce(s, m) != (i == j ? d[i] : 0u)) bad |= 16;
+                }
+                if (bad) atomicOr(&s_bad, bad);
+                __syncthreads();
+                if (s_bad) {
+                        if (tid == 0) { state->check_failed = s_bad; state->halt = 1; state->do_ortho = 0; }
+                        return;
+                }
+        }
+
         // ---- coefficients of orthogonalize (sequential/lanczos_modp.c:460-475)
         //   c     = -(winv * spliced), spliced[:,j] = d[j] ? vtAAv[:,j] : vtAv[:,j]
         //   vtAvd = d[j] ? -vtAv[:,j] : 0

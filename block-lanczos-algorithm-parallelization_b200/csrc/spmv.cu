@@ -10,6 +10,15 @@
 // gather of the x row (V*4 bytes per lane, n_pad*4 contiguous bytes per group).  U steps are
 // software-unrolled so that U independent gathers are in flight per lane.
 // HBM bytes per entry: 8 (matrix) + 4*n_pad (x row, when x does not fit L2) -- see DESIGN.md.
+//
+// Fused all-gather (PUSH = 1, multi-GPU): the product whose result every GPU needs next writes
+// its finished rows not only to the local y but also, over NVLink, into the same rows of every
+// peer's copy of the block (plain stores through peer-mapped pointers).  Rows of a tile are
+// consecutive, so after its tile a warp re-reads the rows it finalised (L2 hits) and stores them
+// to each peer as coalesced runs of up to 512 bytes; the one row a tile may leave open is pushed
+// by k_spmv_fix when it completes it.  The exchange thus costs no extra kernel, no SMs of its own
+// and is spread evenly over the product -- this replaces the reference's per-iteration
+// Send/Recv + Gatherv of the product result (mpi/lanczos_modp.c:1108-1147).
 #include <cstdlib>
 #include "blk_internal.cuh"
 
@@ -57,11 +66,19 @@ template <int V> __device__ __forceinline__ void store_vec(u32 *p, const u32 (&o
         *reinterpret_cast<typename Vec<V>::T *>(p) = t;
 }
 
-template <int L, int V, int FOLD, int HOT>
+template <int V> __device__ __forceinline__ void load_vec_cg(u32 (&o)[V], const u32 *p)
+{
+        typename Vec<V>::T t = __ldcg(reinterpret_cast<const typename Vec<V>::T *>(p));
+        const u32 *w = reinterpret_cast<const u32 *>(&t);
+#pragma unroll
+        for (int k = 0; k < V; k++) o[k] = w[k];
+}
+
+template <int L, int V, int FOLD, int HOT, int PUSH>
 __global__ void __launch_bounds__(WARPS * 32)
 k_spmv(const uint2 *__restrict__ ent, const u32 *__restrict__ chunk_row, u32 *__restrict__ whead,
        int64_t tile0, int64_t ntiles, int Q, u32 rows, const u32 *__restrict__ x, u32 *__restrict__ y, ModP m,
-       const DevSmall *__restrict__ state, u32 hot)
+       const DevSmall *__restrict__ state, u32 hot, PushTargets push)
 {
         u64 pol_hot = 0, pol_cold = 0;
         if (HOT) {
@@ -79,6 +96,7 @@ k_spmv(const uint2 *__restrict__ ent, const u32 *__restrict__ chunk_row, u32 *__
         const u32 cr = __ldg(chunk_row + t * G + g);
         u32 row = cr & 0x7fffffffu;
         bool head_open = (cr >> 31) != 0;
+        const u32 first_started = row + (head_open ? 1u : 0u);      // (group 0's value is the tile's)
         const uint2 *e = ent + t * G * Q + g;
         const u32 *xs = x + sub * V;
         u32 *ys = y + sub * V;
@@ -171,6 +189,23 @@ k_spmv(const uint2 *__restrict__ ent, const u32 *__restrict__ chunk_row, u32 *__
                 store_vec<V>(ys + (size_t)row * NP, o);
         }
         if (g == 0 && head_type != 0) store_vec<V>(whead + t * NP + sub * V, headv);
+
+        if (PUSH) {
+                // Rows this warp has finalised: every row that STARTS in the tile, except the one still open at
+                // its end (that one is finished -- and pushed -- by k_spmv_fix).  They are consecutive:
+                // [first row started by group 0, the row the last group stands on).
+                const u32 ra = __shfl_sync(0xffffffffu, first_started, 0);
+                u32 rb = __shfl_sync(0xffffffffu, row, 31);
+                if (rb > rows) rb = rows;
+                __syncwarp();                                    // the warp's own stores to y, made by other lanes
+                for (u32 r = ra + g; r < rb; r += G) {
+                        u32 o[V];
+                        load_vec_cg<V>(o, ys + (size_t)r * NP);
+#pragma unroll
+                        for (int q = 0; q < PushTargets::MAX; q++)
+                                if (q < push.n) store_vec<V>(push.y[q] + (size_t)r * NP + sub * V, o);
+                }
+        }
 }
 
 // rows that cross tile borders: y[row] (partial left by the tile where the row starts) plus the
@@ -179,7 +214,7 @@ template <int L, int V>
 __global__ void __launch_bounds__(256)
 k_spmv_fix(const u32 *__restrict__ tail_row, const u32 *__restrict__ span, const u32 *__restrict__ whead,
            int64_t scan_lo, int64_t tile_lo, int64_t tile_hi, u32 *__restrict__ y, ModP m,
-           const DevSmall *__restrict__ state)
+           const DevSmall *__restrict__ state, PushTargets push)
 {
         // finishes the rows that END in tiles [tile_lo, tile_hi); such a row starts in a tile >= scan_lo
         constexpr int NP = L * V;
@@ -207,47 +242,58 @@ k_spmv_fix(const u32 *__restrict__ tail_row, const u32 *__restrict__ span, const
 #pragma unroll
         for (int k = 0; k < V; k++) cur[k] = mp_reduce(s[k], m);
         store_vec<V>(y + (size_t)r * NP + sub * V, cur);
+        for (int q = 0; q < push.n; q++) store_vec<V>(push.y[q] + (size_t)r * NP + sub * V, cur);
 }
 
-template <int L, int V, int HOT>
+template <int L, int V, int HOT, int PUSH>
 void launch_hot(const SpOp &op, const ModP &m, const u32 *x, u32 *y, const DevSmall *state, cudaStream_t st,
-                int64_t t0, int64_t t1)
+                int64_t t0, int64_t t1, const PushTargets &push)
 {
         unsigned blocks = (unsigned)((t1 - t0 + WARPS - 1) / WARPS);
         if (blocks == 0) return;
         switch (m.fold_every) {
-        case 0: k_spmv<L, V, 0, HOT><<<blocks, WARPS * 32, 0, st>>>(op.ent, op.chunk_row, op.whead, t0, t1, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols); break;
-        case 8: k_spmv<L, V, 8, HOT><<<blocks, WARPS * 32, 0, st>>>(op.ent, op.chunk_row, op.whead, t0, t1, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols); break;
-        default: k_spmv<L, V, 2, HOT><<<blocks, WARPS * 32, 0, st>>>(op.ent, op.chunk_row, op.whead, t0, t1, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols); break;
+        case 0: k_spmv<L, V, 0, HOT, PUSH><<<blocks, WARPS * 32, 0, st>>>(op.ent, op.chunk_row, op.whead, t0, t1, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols, push); break;
+        case 8: k_spmv<L, V, 8, HOT, PUSH><<<blocks, WARPS * 32, 0, st>>>(op.ent, op.chunk_row, op.whead, t0, t1, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols, push); break;
+        default: k_spmv<L, V, 2, HOT, PUSH><<<blocks, WARPS * 32, 0, st>>>(op.ent, op.chunk_row, op.whead, t0, t1, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols, push); break;
         }
 }
 
 template <int L, int V>
-int launch_lv(const SpOp &op, const ModP &m, const u32 *x, u32 *y, const DevSmall *state, cudaStream_t st, int piece)
+int launch_lv(const SpOp &op, const ModP &m, const u32 *x, u32 *y, const DevSmall *state, cudaStream_t st, int piece,
+              const PushTargets *push)
 {
+        if (op.rows <= 0) return 0;                    // an empty shard (more ranks than rows): nothing to produce
         int64_t t0 = 0, t1 = op.ntiles, scan = 0;
         if (piece >= 0) { t0 = op.piece_tile[piece]; t1 = op.piece_tile[piece + 1]; scan = op.piece_scan[piece]; }
-        if (V == 4 && op.hot_cols > 0) launch_hot<L, V, 1>(op, m, x, y, state, st, t0, t1);
-        else launch_hot<L, V, 0>(op, m, x, y, state, st, t0, t1);
+        const PushTargets none;
+        const bool hot = V == 4 && op.hot_cols > 0;
+        if (push && push->n > 0) {
+                if (hot) launch_hot<L, V, 1, 1>(op, m, x, y, state, st, t0, t1, *push);
+                else launch_hot<L, V, 0, 1>(op, m, x, y, state, st, t0, t1, *push);
+        } else {
+                if (hot) launch_hot<L, V, 1, 0>(op, m, x, y, state, st, t0, t1, none);
+                else launch_hot<L, V, 0, 0>(op, m, x, y, state, st, t0, t1, none);
+        }
         int64_t threads = (t1 - scan) * L;
         if (threads > 0)
-                k_spmv_fix<L, V><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(op.tail_row, op.span, op.whead, scan, t0, t1, y, m, state);
+                k_spmv_fix<L, V><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(op.tail_row, op.span, op.whead, scan, t0, t1, y, m, state,
+                                                                                   push ? *push : none);
         return 2;
 }
 
 }  // namespace
 
 int launch_spmv(const SpOp &op, const Geometry &geo, const ModP &m, const u32 *x, u32 *y,
-                const DevSmall *state, cudaStream_t st, int piece)
+                const DevSmall *state, cudaStream_t st, int piece, const PushTargets *push)
 {
         switch (geo.np) {
-        case 1: return launch_lv<1, 1>(op, m, x, y, state, st, piece);
-        case 2: return launch_lv<1, 2>(op, m, x, y, state, st, piece);
-        case 4: return launch_lv<1, 4>(op, m, x, y, state, st, piece);
-        case 8: return launch_lv<2, 4>(op, m, x, y, state, st, piece);
-        case 16: return launch_lv<4, 4>(op, m, x, y, state, st, piece);
-        case 32: return launch_lv<8, 4>(op, m, x, y, state, st, piece);
-        case 64: return launch_lv<16, 4>(op, m, x, y, state, st, piece);
+        case 1: return launch_lv<1, 1>(op, m, x, y, state, st, piece, push);
+        case 2: return launch_lv<1, 2>(op, m, x, y, state, st, piece, push);
+        case 4: return launch_lv<1, 4>(op, m, x, y, state, st, piece, push);
+        case 8: return launch_lv<2, 4>(op, m, x, y, state, st, piece, push);
+        case 16: return launch_lv<4, 4>(op, m, x, y, state, st, piece, push);
+        case 32: return launch_lv<8, 4>(op, m, x, y, state, st, piece, push);
+        case 64: return launch_lv<16, 4>(op, m, x, y, state, st, piece, push);
         }
         return -1;
 }

@@ -16,7 +16,9 @@
  * Deviations from the reference, all documented in DESIGN.md:
  *   - p may be as large as 2^31-1 (the reference stops at 2^30-35);
  *   - n <= 64;
- *   - checkpoint files are written through rename() (never torn);
+ *   - checkpoint files are formatted into *.tmp and renamed into place together, with a commit
+ *     marker (checkpoint.commit) that --load-checkpoint verifies;
+ *   - BLK_GPUS=G in the environment shards the job over G GPUs of the box (same files, same output);
  *   - the GPU runs iterations in batches, so progress is reported per batch.
  */
 #define _POSIX_C_SOURCE 200809L
@@ -208,21 +210,42 @@ struct snapshot {
         bool running;
 };
 
+/* "checkpoint.commit" -- a sidecar next to the reference's five files: "pending K" while the files of
+ * snapshot K are being renamed into place, "complete K" afterwards.  --load-checkpoint refuses a set that
+ * is not marked complete for the iteration verbosity.txt names (a crash between two renames would otherwise
+ * resume from v of one snapshot and p of another).  Checkpoints written by the reference program have no
+ * sidecar and are accepted as they are. */
+static void write_commit_marker(const char *state, int n_iterations)
+{
+        FILE *f = fopen("checkpoint.commit.tmp", "w");
+        if (!f)
+                err(1, "cannot open %s", "checkpoint.commit");
+        fprintf(f, "%s %d\n", state, n_iterations);
+        if (fclose(f) != 0 || rename("checkpoint.commit.tmp", "checkpoint.commit") != 0)
+                err(1, "cannot write %s", "checkpoint.commit");
+}
+
 static void *snapshot_writer(void *arg)
 {
         struct snapshot *s = arg;
+        static const char *names[4] = {"v.txt", "tmp.txt", "Av.txt", "p.txt"};
+        /* all five files are formatted into *.tmp first (the slow part) ... */
+        for (int k = 0; k < 4; k++)
+                vector_write_tmp(names[k], s->pad, s->blk[k]);
         /* verbosity.txt: n_iterations, start, now (openMP/lanczos_modp.c:591-609) */
         FILE *f = fopen("verbosity.txt.tmp", "w");
         if (!f)
                 err(1, "cannot open %s", "verbosity.txt");
         printf("\t\t>> Saving verbosity engine infos in %s\n", "verbosity.txt");
         fprintf(f, "%d\n%f\n%f\n", s->n_iterations, s->t_start, s->t_now);
-        fclose(f);
-        if (rename("verbosity.txt.tmp", "verbosity.txt") != 0)
+        if (fclose(f) != 0)
                 err(1, "cannot write verbosity.txt");
-        static const char *names[4] = {"v.txt", "tmp.txt", "Av.txt", "p.txt"};
+        /* ... and renamed into place together, verbosity.txt last */
+        write_commit_marker("pending", s->n_iterations);
         for (int k = 0; k < 4; k++)
-                vector_save(names[k], s->pad, s->blk[k]);
+                commit_tmp(names[k]);
+        commit_tmp("verbosity.txt");
+        write_commit_marker("complete", s->n_iterations);
         return NULL;
 }
 
@@ -267,7 +290,31 @@ static int read_checkpoint_info(double *extra)
                 errx(1, "verbosity.txt is malformed");
         fclose(f);
         *extra = (double)((int)b - (int)a);     /* the reference truncates both to int (:645-673) */
+        f = fopen("checkpoint.commit", "r");
+        if (f) {
+                char state[32] = "";
+                int marked = -1;
+                if (fscanf(f, "%31s %d", state, &marked) != 2 || strcmp(state, "complete") != 0 || marked != it)
+                        errx(1, "the checkpoint files are not one complete snapshot (checkpoint.commit: \"%s %d\", "
+                                "verbosity.txt: iteration %d); refusing to resume", state, marked, it);
+                fclose(f);
+        }
         return it;
+}
+
+/* ---- multi-GPU: BLK_GPUS=G in the environment runs the job on G GPUs of this box (devices BLK_DEVICE ...),
+ * all driven by this one process through a single context (blk_params.rank = BLK_RANK_ALL) -- the counterpart
+ * of `mpirun -np G` for the reference's MPI build (mpi/lanczos_modp.c:1829-1863).  No new option: the command
+ * line stays the reference's. */
+static int gpus_from_env(void)
+{
+        const char *e = getenv("BLK_GPUS");
+        if (!e || !e[0])
+                return 1;
+        int g = atoi(e);
+        if (g < 1 || g > 64)
+                errx(1, "BLK_GPUS must be a number of GPUs between 1 and 64");
+        return g;
 }
 
 int main(int argc, char **argv)
@@ -301,11 +348,16 @@ int main(int argc, char **argv)
         prm.nrows = M.nrows; prm.ncols = M.ncols; prm.nnz = M.nnz;
         prm.Mi = M.i; prm.Mj = M.j; prm.Mx = M.x;
         prm.n = n; prm.prime = (uint32_t)o.prime; prm.right_kernel = o.right;
-        prm.device = o.device; prm.rank = 0; prm.world = 1; prm.use_graph = -1;
+        const int gpus = gpus_from_env();
+        prm.device = o.device; prm.use_graph = -1;
+        prm.world = gpus; prm.rank = gpus > 1 ? BLK_RANK_ALL : 0;
         blk_ctx *ctx = NULL;
         double t_build = wall();
         GPU(blk_create(&ctx, &prm));
-        printf("  - Matrix resident on GPU %d in %.2fs\n", o.device, wall() - t_build);
+        if (gpus > 1)
+                printf("  - Matrix resident on GPUs %d-%d (row blocks) in %.2fs\n", o.device, o.device + gpus - 1, wall() - t_build);
+        else
+                printf("  - Matrix resident on GPU %d in %.2fs\n", o.device, wall() - t_build);
         mtx_free(&M);                                    /* the device owns the matrix now */
 
         struct progress pg = {0};

@@ -301,7 +301,7 @@ void kernel_block_save(const char *filename, int nrows, int n, const uint32_t *v
                 err(1, "cannot write %s", filename);
 }
 
-void vector_save(const char *filename, long count, const uint32_t *v)
+void vector_write_tmp(const char *filename, long count, const uint32_t *v)
 {
         char tmpname[4096];
         snprintf(tmpname, sizeof(tmpname), "%s.tmp", filename);
@@ -312,8 +312,20 @@ void vector_save(const char *filename, long count, const uint32_t *v)
         write_lines(f, tmpname, count, 1, v);
         if (fclose(f) != 0)
                 err(1, "cannot write %s", tmpname);
+}
+
+void commit_tmp(const char *filename)
+{
+        char tmpname[4096];
+        snprintf(tmpname, sizeof(tmpname), "%s.tmp", filename);
         if (rename(tmpname, filename) != 0)
                 err(1, "cannot rename %s to %s", tmpname, filename);
+}
+
+void vector_save(const char *filename, long count, const uint32_t *v)
+{
+        vector_write_tmp(filename, count, v);
+        commit_tmp(filename);
 }
 
 void vector_load(const char *filename, long count, uint32_t *v)
@@ -329,7 +341,14 @@ void vector_load(const char *filename, long count, uint32_t *v)
                              filename, count);
                 v[got++] = (uint32_t)(int)val;
         }
-        for (; got < count; got++)
-                v[got] = 0;
+        /* a checkpoint block is exactly block_size_pad lines (openMP/lanczos_modp.c:571-589): anything else is a
+         * truncated or foreign file and must not be resumed from */
+        while (p < end && (*p == ' ' || *p == '\t' || *p == '\r' || *p == '\n'))
+                p++;
+        if (p < end)
+                errx(1, "%s: unexpected text after %ld values", filename, got);
+        if (got != count)
+                errx(1, "%s holds %ld values, expected %ld (truncated checkpoint, or matrix / --n / side differ)",
+                     filename, got, count);
         free(buf);
 }

@@ -29,5 +29,8 @@ void kernel_block_save(const char *filename, int nrows, int n, const uint32_t *v
 /* checkpoint vectors (openMP/lanczos_modp.c:573-589, 611-635): `count` lines of "%d\n".
  * Saving goes through a temporary file + rename so a crash never leaves a torn file. */
 void vector_save(const char *filename, long count, const uint32_t *v);
+/* the two halves of vector_save: write "<filename>.tmp", then rename it over <filename> */
+void vector_write_tmp(const char *filename, long count, const uint32_t *v);
+void commit_tmp(const char *filename);
 void vector_load(const char *filename, long count, uint32_t *v);
 #endif

@@ -42,6 +42,9 @@ extern "C" {
 #define BLK_ABI_VERSION 1
 #define BLK_MAX_N 64
 #define BLK_NCCL_ID_BYTES 128
+/* blk_params.rank value: this process drives ALL `world` GPUs (devices device ... device+world-1) through one
+ * context; the library runs one host thread per GPU inside every call (nccl_id is not needed). */
+#define BLK_RANK_ALL (-1)
 
 typedef struct blk_ctx blk_ctx;
 
@@ -60,7 +63,8 @@ typedef struct blk_params {
         uint32_t prime;           /* modulus (global `prime`) */
         int32_t  right_kernel;    /* 0: --left (x*M == 0), 1: --right (M*x == 0) */
         int32_t  device;          /* CUDA device ordinal */
-        int32_t  rank, world;     /* this context's row shard of a `world`-GPU job (0,1: single GPU) */
+        int32_t  rank, world;     /* this context's row shard of a `world`-GPU job (0,1: single GPU);
+                                     rank = BLK_RANK_ALL: one context for the whole job (single process) */
         const void *nccl_id;      /* BLK_NCCL_ID_BYTES from blk_nccl_unique_id (rank 0), if world > 1 */
         void    *stream;          /* cudaStream_t to run on, or NULL for a private stream */
         int32_t  chunk_len;       /* entries per lane-group chunk of the sparse layout; 0 = auto */
@@ -110,10 +114,14 @@ int64_t blk_block_pad(int32_t nrows, int32_t ncols, int32_t n, int32_t right_ker
 /* ---- the iteration (block_lanczos main loop, :631-659) ---------------- */
 /* Load the Lanczos state: v and p hold N*n u32 (N = nrows for --left, ncols for
  * --right); p may be NULL (all zero: fresh start).  n_iterations is the
- * reference's counter (non-zero after --load-checkpoint).                 */
+ * reference's counter (non-zero after --load-checkpoint).  In a multi-GPU job
+ * every rank is given the same full-length blocks but reads only the rows it owns
+ * (1/world of the PCIe traffic); the rest reaches it from the peers over NVLink. */
 int  blk_set_state(blk_ctx *ctx, const uint32_t *v, const uint32_t *p, int32_t n_iterations);
 /* Run up to max_iters further iterations entirely on the device (no host
- * round-trip per iteration).  Stops early, exactly like the reference, at the
+ * round-trip per iteration).  With BLK_CHECK=1 in the environment at blk_create time the n x n stage also
+ * evaluates the reference's correctness_tests (:532-557) on every iteration; a violated invariant stops the
+ * loop before anything is updated and this call fails (the reference aborts on the assert).  Stops early, exactly like the reference, at the
  * iteration whose semi_inverse returns 0 pivots (:644,:649): v is then left
  * untouched and tmp = M^T v (resp. M v).  *stopped is that condition,
  * *iters_total the reference's n_iterations afterwards.                    */
@@ -122,6 +130,11 @@ int  blk_iterate(blk_ctx *ctx, int32_t max_iters, int32_t *iters_total, int32_t 
  * (blk_block_pad u32 each; any pointer may be NULL).  Contents are identical
  * to the reference's v/tmp/Av/p at the same point of the loop.             */
 int  blk_get_state(blk_ctx *ctx, uint32_t *v, uint32_t *tmp, uint32_t *Av, uint32_t *p);
+/* Multi-GPU jobs with one process per GPU: like blk_get_state for v, Av, p (any may be NULL; same padded
+ * layout), but only the rows this rank owns -- [local_N0, local_N1) of blk_get_info -- are written, nothing
+ * crosses NVLink and each rank moves 1/world of the data over PCIe (a distributed checkpoint).  On a single
+ * GPU, and on a BLK_RANK_ALL context, identical to blk_get_state. */
+int  blk_get_state_local(blk_ctx *ctx, uint32_t *v, uint32_t *Av, uint32_t *p);
 /* final_check (sequential/lanczos_modp.c:560-582) on the device, without copying the blocks back:
  * *v_nonzero = (v != 0) over the N rows, *vtm_zero = (tmp == 0) over the Mc rows, where tmp is the
  * product M^T v (resp. M v) of the current v -- the state the loop is in after it stopped on

@@ -320,12 +320,12 @@ def test_device_side_final_check_and_checker(lib, oracle):
         assert not oracle.sparse_matrix_vector_product(M, V, True, n, p).any()
 
 
-@pytest.mark.skipif(not os.environ.get("BLK_TEST_EXPERIMENTAL"), reason="experimental path: set BLK_TEST_EXPERIMENTAL=1")
 @pytest.mark.parametrize("K", [2, 3, 5])
 def test_column_blocked_products_single_gpu(lib, oracle, monkeypatch, K):
     """BLK_COLBLOCKS=K on one GPU: every product runs as K-1 column blocks over all rows plus a last column
     block cut into K row pieces, summed mod p by the combine kernel (the building blocks of the arrival-order
     multi-GPU exchange, context.cu).  Whole runs must stay bit-identical to the oracle."""
+    monkeypatch.setenv("BLK_EXPERIMENTAL", "1")          # a validated but non-default mode: explicit opt-in
     monkeypatch.setenv("BLK_COLBLOCKS", str(K))
     s = lib.synth
     cases = [(s.powerlaw_rows(900, 800, mean=7, seed=2, with_empty_rows=40, order="file"), 4, P_FERMAT, False, -1),
@@ -341,3 +341,34 @@ def test_column_blocked_products_single_gpu(lib, oracle, monkeypatch, K):
         assert got["iters"] == want["iters"] and got["stopped"] == want["stopped"]
         for k in ("v", "tmp", "Av", "p"):
             assert np.array_equal(got[k], want[k]), (K, n, k)
+
+
+def test_runtime_correctness_tests(lib, oracle, monkeypatch):
+    """BLK_CHECK=1: the n x n stage evaluates the reference's correctness_tests (sequential/lanczos_modp.c:532-557,
+    called on every iteration at :647) on the device.  Clean runs are unaffected (bit-identical to the oracle);
+    a corrupted vtAv (fault injection, BLK_CHECK_FAULT=k) stops the loop in iteration k before anything is
+    updated and blk_iterate fails, as the reference's assert would."""
+    monkeypatch.setenv("BLK_CHECK", "1")
+    s = lib.synth
+    for M, n, p, right in ((s.powerlaw_rows(900, 800, mean=7, seed=2), 4, P_FERMAT, False),
+                           (s.uniform_nnz(2500, 3100, 30000, seed=4, order="col"), 16, P_MERSENNE, True),
+                           (s.uniform_rows(400, 380, 6, seed=3), 1, P_CAP, False)):
+        Mp = M.reduced(p)
+        N = M.ncols if right else M.nrows
+        v0 = oracle.start_block(N * n, p)
+        for graph in (0, 1):
+            with lib.BlockLanczos(Mp, n=n, prime=p, right=right, use_graph=graph) as ctx:
+                got = ctx.block_lanczos(v0, stop_after=12, batch=5)
+            want = oracle.lanczos_run(Mp, n, p, right, stop_after=12)
+            for k in ("v", "tmp", "Av", "p"):
+                assert np.array_equal(got[k], want[k]), (n, graph, k)
+        monkeypatch.setenv("BLK_CHECK_FAULT", "6")
+        with lib.BlockLanczos(Mp, n=n, prime=p, right=right) as ctx:
+            ctx.set_state(v0)
+            with pytest.raises(lib.BlkError, match="correctness_tests failed in iteration 6"):
+                ctx.iterate(20)
+            # the state is the one before the failing iteration: 5 completed iterations
+            st = ctx.get_state(("v", "p"))
+            want = oracle.lanczos_run(Mp, n, p, right, stop_after=5)
+            assert np.array_equal(st["v"], want["v"]) and np.array_equal(st["p"], want["p"])
+        monkeypatch.delenv("BLK_CHECK_FAULT")
