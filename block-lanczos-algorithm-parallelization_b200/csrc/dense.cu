@@ -358,8 +358,8 @@ int launch_small(const Geometry &geo, const ModP &m, u64 *sums, u32 *mats, DevSm
 int launch_ortho(const Geometry &geo, const ModP &m, int64_t rows, u32 *v, const u32 *Av, u32 *p,
                  u32 *v_out, u32 *p_out, const u32 *mats, const DevSmall *state, int force, cudaStream_t st)
 {
-        if (rows <= 0) return 0;
-        if (dense_umma_supported(geo.np, rows)) {
+        if (rows == 0) return 0;          // (rows < 0 is the prepare-only call of dense_prepare)
+        if (rows > 0 && dense_umma_supported(geo.np, rows)) {
                 int k = launch_ortho_umma(geo.np, m, rows, v, Av, p, v_out, p_out, mats, state, force, st);
                 if (k > 0) return k;
         }

@@ -36,6 +36,8 @@ def main():
     ap.add_argument("--right", type=int, default=0)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--spmv-reps", type=int, default=0,
+                    help="also time sparse_matrix_vector_product alone (both directions), this many calls each")
     a = ap.parse_args()
 
     try:
@@ -58,6 +60,7 @@ def main():
     kind = "reference"
     path = os.path.join(HERE, "_ref", f"libref_{a.lib}.so")
     times = []
+    spmv = None
     if a.lib != "port" and os.path.exists(path):
         L = C.CDLL(path)
 
@@ -78,6 +81,22 @@ def main():
             v = L.block_lanczos(C.byref(m), a.n, bool(a.right))
             times.append(time.perf_counter() - t)
             libc.free(v)
+        if a.spmv_reps > 0:
+            # the reference's own SpMV (sequential/lanczos_modp.c:266 / openMP/lanczos_modp.c:329), timed alone
+            pad = max(-(-M.nrows // a.n), -(-M.ncols // a.n)) * a.n * a.n
+            rng = np.random.default_rng(3)
+            x = rng.integers(0, a.prime, size=pad, dtype=np.uint64).astype(np.uint32)
+            y = np.zeros(pad, dtype=np.uint32)
+            # (the OpenMP variant takes block_size_pad as a fifth argument, openMP/lanczos_modp.c:329)
+            extra = [C.c_long(pad)] if a.lib == "omp" else []
+            L.sparse_matrix_vector_product.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_bool] + ([C.c_long] if extra else [])
+            spmv = {}
+            for tr in (False, True):
+                L.sparse_matrix_vector_product(y.ctypes.data, C.byref(m), x.ctypes.data, tr, *extra)          # warm-up
+                t = time.perf_counter()
+                for _ in range(a.spmv_reps):
+                    L.sparse_matrix_vector_product(y.ctypes.data, C.byref(m), x.ctypes.data, tr, *extra)
+                spmv["Mt_x" if tr else "M_x"] = (time.perf_counter() - t) / a.spmv_reps
     else:
         kind, threads = "port", 1
         from oracle.oracle import Oracle
@@ -89,9 +108,13 @@ def main():
     sys.stdout.flush()
     os.dup2(saved, 1)
     sec = times[-1]
-    print(json.dumps(dict(kind=kind, lib=a.lib, threads=threads, rows=a.rows, cols=a.cols, nnz=M.nnz, n=a.n,
-                          prime=a.prime, iters=a.iters, seconds=sec, iters_per_s=a.iters / sec,
-                          gnnzn_per_s=2.0 * M.nnz * a.n * a.iters / sec / 1e9)))
+    out = dict(kind=kind, lib=a.lib, threads=threads, host_cores=os.cpu_count(), rows=a.rows, cols=a.cols, nnz=M.nnz, n=a.n,
+               prime=a.prime, iters=a.iters, seconds=sec, iters_per_s=a.iters / sec,
+               gnnzn_per_s=2.0 * M.nnz * a.n * a.iters / sec / 1e9)
+    if spmv:
+        out["spmv_seconds"] = spmv
+        out["spmv_gnnzn_per_s"] = {k: M.nnz * a.n / t / 1e9 for k, t in spmv.items()}
+    print(json.dumps(out))
 
 
 if __name__ == "__main__":
