@@ -2,7 +2,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdlib>
 #include <string>
+#include <utility>
 #include <vector>
 #include "modp.cuh"
 
@@ -91,6 +93,47 @@ static inline int blk_sm_count()
         }
         return cache[dev];
 }
+
+// ---- programmatic dependent launch -------------------------------------------------------------
+// The kernels of one iteration form a chain in one stream (or one CUDA graph).  Every one of them starts with
+// pdl_prologue(): "launch_dependents" lets the next kernel of the chain be scheduled -- its blocks become
+// resident and run their own prologue -- while this one is still working, and "wait" blocks until the
+// previous kernel has finished and its writes are visible.  Nothing is read or written before the wait, so
+// the results are those of the serial chain; what disappears is the launch latency between two kernels,
+// which is most of an iteration on the L2-resident configurations (BASELINE configs 1-3).
+// launch_k() launches with the attribute that allows this overlap when BLK_PDL=1.  Measured on configs 1-3
+// (gpurun_out/r2_e_small_pdl*.json, profiles/r02_small_configs.txt): 26.1 / 43.6 / 72.1 us per iteration with it,
+// 25.0 / 41.4 / 73.6 without -- inside a CUDA graph the gap between two kernel nodes is already hidden, what an
+// iteration pays is the latency chain inside each of its six kernels.  So the overlap is OFF by default.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_prologue()
+{
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+static inline bool blk_pdl_enabled()
+{
+        static int on = -1;
+        if (on < 0) {
+                const char *e = getenv("BLK_PDL");
+                on = e && e[0] == '1';
+        }
+        return on != 0;
+}
+
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args)
+{
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = blk_pdl_enabled() ? 1 : 0;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+#endif
 
 // ---- launchers (each returns the number of kernels it launched) ---------------------------
 // layout_build.cu

@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(DOTS_TB)
 k_dots(int64_t rows, const u32 *__restrict__ v, const u32 *__restrict__ Av, unsigned long long *sums,
        ModP m, const DevSmall *state, SmallFuse fuse)
 {
+        pdl_prologue();
         constexpr int TI = NP < 4 ? NP : 4;
         constexpr int PER = NP / TI;          // tiles per dimension
         constexpr int T = PER * PER;          // threads per team
@@ -147,6 +148,7 @@ __global__ void __launch_bounds__(SMALL_TB)
 k_small(int n, int np, unsigned long long *__restrict__ sums, u32 *__restrict__ mats,
         DevSmall *__restrict__ state, int mode, ModP m)
 {
+        pdl_prologue();
         extern __shared__ u32 sm_small[];
         small_body(n, np, sums, mats, state, mode, m, sm_small);
 }
@@ -165,6 +167,7 @@ __global__ void __launch_bounds__(ORTHO_TB)
 k_ortho(int64_t rows, const u32 *v, const u32 *__restrict__ Av, const u32 *p, u32 *v_out, u32 *p_out,
         const u32 *__restrict__ mats, ModP m, const DevSmall *__restrict__ state, int force)
 {
+        pdl_prologue();
         constexpr int TPR = NP / JT;
         constexpr int KV = NP < 4 ? NP : 4;
         constexpr int JV = JT < 4 ? JT : 4;
@@ -279,9 +282,9 @@ int dots_fold(const ModP &m, int64_t rows, const u32 *v, const u32 *Av, u64 *sum
 {
         size_t smem = fuse.counter ? sizeof(u32) * small_smem_words(fuse.n) : 0;
         switch (m.fold_every) {
-        case 0: k_dots<NP, 0><<<nblocks, DOTS_TB, smem, st>>>(rows, v, Av, (unsigned long long *)sums, m, state, fuse); break;
-        case 8: k_dots<NP, 8><<<nblocks, DOTS_TB, smem, st>>>(rows, v, Av, (unsigned long long *)sums, m, state, fuse); break;
-        default: k_dots<NP, 2><<<nblocks, DOTS_TB, smem, st>>>(rows, v, Av, (unsigned long long *)sums, m, state, fuse); break;
+        case 0: launch_k(k_dots<NP, 0>, nblocks, DOTS_TB, smem, st, rows, v, Av, (unsigned long long *)sums, m, state, fuse); break;
+        case 8: launch_k(k_dots<NP, 8>, nblocks, DOTS_TB, smem, st, rows, v, Av, (unsigned long long *)sums, m, state, fuse); break;
+        default: launch_k(k_dots<NP, 2>, nblocks, DOTS_TB, smem, st, rows, v, Av, (unsigned long long *)sums, m, state, fuse); break;
         }
         return 1;
 }
@@ -298,7 +301,7 @@ void ortho_go(int64_t rows, u32 *v, const u32 *Av, u32 *p, u32 *v_out, u32 *p_ou
         }
         int64_t threads = rows * (NP / JT);
         unsigned blocks = (unsigned)((threads + ORTHO_TB - 1) / ORTHO_TB);
-        k_ortho<NP, JT, FOLD><<<blocks, ORTHO_TB, smem, st>>>(rows, v, Av, p, v_out, p_out, mats, m, state, force);
+        launch_k(k_ortho<NP, JT, FOLD>, blocks, ORTHO_TB, smem, st, rows, v, Av, p, v_out, p_out, mats, m, state, force);
 }
 
 template <int NP, int JT>
@@ -351,7 +354,7 @@ int launch_small(const Geometry &geo, const ModP &m, u64 *sums, u32 *mats, DevSm
                  cudaStream_t st)
 {
         size_t smem = sizeof(u32) * small_smem_words(geo.n);
-        k_small<<<1, SMALL_TB, smem, st>>>(geo.n, geo.np, (unsigned long long *)sums, mats, state, mode, m);
+        launch_k(k_small, 1, SMALL_TB, smem, st, geo.n, geo.np, (unsigned long long *)sums, mats, state, mode, m);
         return 1;
 }
 

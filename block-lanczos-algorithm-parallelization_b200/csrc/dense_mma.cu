@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(128)
 k_ortho_mma(int64_t rows, const u32 *v, const u32 *__restrict__ Av, const u32 *p, u32 *v_out, u32 *p_out,
             const u32 *__restrict__ mats, ModP m, const DevSmall *__restrict__ state, int force)
 {
+        pdl_prologue();
         constexpr int T = NP / 8, S = NP / 8, WPT = NP / 4;
         constexpr int FRAG = 12 * T * S * 64;
         extern __shared__ u32 sm[];
@@ -188,6 +189,7 @@ __global__ void __launch_bounds__(128)
 k_dots_mma(int64_t rows, const u32 *__restrict__ v, const u32 *__restrict__ Av,
            unsigned long long *sums, ModP m, const DevSmall *state, SmallFuse fuse)
 {
+        pdl_prologue();
         constexpr int CB = NP < 16 ? NP : 16;          // columns per block (8 or 16)
         constexpr int NB = NP / CB;                    // column blocks per dimension
         constexpr int MT = CB == 16 ? 4 : 2;           // m-tiles: CB=16 one per limb a; CB=8 two limbs per tile
@@ -331,7 +333,7 @@ int ortho_go(int64_t rows, u32 *v, const u32 *Av, u32 *p, u32 *v_out, u32 *p_out
         int64_t cap = (int64_t)blk_sm_count() * (NP == 32 ? 4 : 8);
         if (blocks > cap) blocks = cap;
         if (blocks < 1) blocks = 1;
-        k_ortho_mma<NP><<<(unsigned)blocks, 128, ortho_smem<NP>(), st>>>(rows, v, Av, p, v_out, p_out, mats, m, state, force);
+        launch_k(k_ortho_mma<NP>, (unsigned)blocks, 128, ortho_smem<NP>(), st, rows, v, Av, p, v_out, p_out, mats, m, state, force);
         return 1;
 }
 
@@ -347,7 +349,7 @@ int dots_go(int64_t rows, const u32 *v, const u32 *Av, u64 *sums, const ModP &m,
         if (bx < 1) bx = 1;
         dim3 grid((unsigned)bx, NB * NB);
         size_t smem = fuse.counter ? sizeof(u32) * small_smem_words(fuse.n) : 0;
-        k_dots_mma<NP><<<grid, 128, smem, st>>>(rows, v, Av, (unsigned long long *)sums, m, state, fuse);
+        launch_k(k_dots_mma<NP>, grid, 128, smem, st, rows, v, Av, (unsigned long long *)sums, m, state, fuse);
         return 1;
 }
 

@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 k_dots_umma(const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_av, int64_t ntile,
             unsigned long long *sums, ModP m, const DevSmall *state, SmallFuse fuse)
 {
+        pdl_prologue();
         constexpr int NP = 16;
         constexpr uint32_t BUF_COLS = WIDE ? 64 : 128;         // TMEM columns of one accumulator set
         extern __shared__ uint8_t dyn_raw[];
@@ -356,6 +357,7 @@ k_ortho_umma(const __grid_constant__ CUtensorMap map_v, const __grid_constant__ 
              const __grid_constant__ CUtensorMap map_pout, int64_t ntile, const u32 *__restrict__ mats, ModP m,
              const DevSmall *__restrict__ state, int force)
 {
+        pdl_prologue();
         constexpr int NP = 16;
         constexpr int EPI = 2 * 4 * 64 / CW;                        // epilogue warps
         constexpr int NTHR = (EPI + 3) * 32;                        // + producer, MMA issuer, store warp
@@ -585,9 +587,9 @@ int launch_dots_umma(int np, const ModP &m, int64_t rows, const u32 *v, const u3
         const unsigned grid = (unsigned)(ntile < blk_sm_count() ? ntile : blk_sm_count());
         if (wide < 0) wide = umma_mode() == 2;
         if (wide)
-                k_dots_umma<true><<<grid, THREADS, DOTS_SMEM, st>>>(mv, ma, ntile, (unsigned long long *)sums, m, state, fuse);
+                launch_k(k_dots_umma<true>, grid, THREADS, DOTS_SMEM, st, mv, ma, ntile, (unsigned long long *)sums, m, state, fuse);
         else
-                k_dots_umma<false><<<grid, THREADS, DOTS_SMEM, st>>>(mv, ma, ntile, (unsigned long long *)sums, m, state, fuse);
+                launch_k(k_dots_umma<false>, grid, THREADS, DOTS_SMEM, st, mv, ma, ntile, (unsigned long long *)sums, m, state, fuse);
         return 1;
 }
 
@@ -605,14 +607,14 @@ int launch_ortho_umma(int np, const ModP &m, int64_t rows, u32 *v, const u32 *Av
         const unsigned grid = (unsigned)(ntile < blk_sm_count() ? ntile : blk_sm_count());
         if (variant < 0) variant = ORTHO_DEFAULT_VARIANT;
         switch (variant) {
-        case 0: k_ortho_umma<64, 5><<<grid, 11 * 32, ortho_smem(5), st>>>(mv, ma, mp, mvo, mpo, ntile, mats, m, state, force); break;
-        case 1: k_ortho_umma<64, 7><<<grid, 11 * 32, ortho_smem(7), st>>>(mv, ma, mp, mvo, mpo, ntile, mats, m, state, force); break;
-        case 2: k_ortho_umma<32, 5><<<grid, 19 * 32, ortho_smem(5), st>>>(mv, ma, mp, mvo, mpo, ntile, mats, m, state, force); break;
-        case 3: k_ortho_umma<32, 7><<<grid, 19 * 32, ortho_smem(7), st>>>(mv, ma, mp, mvo, mpo, ntile, mats, m, state, force); break;
-        case 4: k_ortho_umma<64, 5, true><<<grid, 11 * 32, ortho_smem(5), st>>>(mv, ma, mp, mvo, mpo, ntile, mats, m, state, force); break;
-        case 5: k_ortho_umma<64, 7, true><<<grid, 11 * 32, ortho_smem(7), st>>>(mv, ma, mp, mvo, mpo, ntile, mats, m, state, force); break;
-        case 6: k_ortho_umma<32, 5, true><<<grid, 19 * 32, ortho_smem(5), st>>>(mv, ma, mp, mvo, mpo, ntile, mats, m, state, force); break;
-        default: k_ortho_umma<32, 7, true><<<grid, 19 * 32, ortho_smem(7), st>>>(mv, ma, mp, mvo, mpo, ntile, mats, m, state, force); break;
+        case 0: launch_k(k_ortho_umma<64, 5>, grid, 11 * 32, ortho_smem(5), st, mv, ma, mp, mvo, mpo, ntile, mats, m, state, force); break;
+        case 1: launch_k(k_ortho_umma<64, 7>, grid, 11 * 32, ortho_smem(7), st, mv, ma, mp, mvo, mpo, ntile, mats, m, state, force); break;
+        case 2: launch_k(k_ortho_umma<32, 5>, grid, 19 * 32, ortho_smem(5), st, mv, ma, mp, mvo, mpo, ntile, mats, m, state, force); break;
+        case 3: launch_k(k_ortho_umma<32, 7>, grid, 19 * 32, ortho_smem(7), st, mv, ma, mp, mvo, mpo, ntile, mats, m, state, force); break;
+        case 4: launch_k(k_ortho_umma<64, 5, true>, grid, 11 * 32, ortho_smem(5), st, mv, ma, mp, mvo, mpo, ntile, mats, m, state, force); break;
+        case 5: launch_k(k_ortho_umma<64, 7, true>, grid, 11 * 32, ortho_smem(7), st, mv, ma, mp, mvo, mpo, ntile, mats, m, state, force); break;
+        case 6: launch_k(k_ortho_umma<32, 5, true>, grid, 19 * 32, ortho_smem(5), st, mv, ma, mp, mvo, mpo, ntile, mats, m, state, force); break;
+        default: launch_k(k_ortho_umma<32, 7, true>, grid, 19 * 32, ortho_smem(7), st, mv, ma, mp, mvo, mpo, ntile, mats, m, state, force); break;
         }
         return 1;
 }

@@ -80,6 +80,7 @@ k_spmv(const uint2 *__restrict__ ent, const u32 *__restrict__ chunk_row, u32 *__
        int64_t tile0, int64_t ntiles, int Q, u32 rows, const u32 *__restrict__ x, u32 *__restrict__ y, ModP m,
        const DevSmall *__restrict__ state, u32 hot, PushTargets push)
 {
+        pdl_prologue();
         u64 pol_hot = 0, pol_cold = 0;
         if (HOT) {
                 asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_hot));
@@ -216,6 +217,7 @@ k_spmv_fix(const u32 *__restrict__ tail_row, const u32 *__restrict__ span, const
            int64_t scan_lo, int64_t tile_lo, int64_t tile_hi, u32 *__restrict__ y, ModP m,
            const DevSmall *__restrict__ state, PushTargets push)
 {
+        pdl_prologue();
         // finishes the rows that END in tiles [tile_lo, tile_hi); such a row starts in a tile >= scan_lo
         constexpr int NP = L * V;
         if (state && state->halt) return;
@@ -252,9 +254,9 @@ void launch_hot(const SpOp &op, const ModP &m, const u32 *x, u32 *y, const DevSm
         unsigned blocks = (unsigned)((t1 - t0 + WARPS - 1) / WARPS);
         if (blocks == 0) return;
         switch (m.fold_every) {
-        case 0: k_spmv<L, V, 0, HOT, PUSH><<<blocks, WARPS * 32, 0, st>>>(op.ent, op.chunk_row, op.whead, t0, t1, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols, push); break;
-        case 8: k_spmv<L, V, 8, HOT, PUSH><<<blocks, WARPS * 32, 0, st>>>(op.ent, op.chunk_row, op.whead, t0, t1, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols, push); break;
-        default: k_spmv<L, V, 2, HOT, PUSH><<<blocks, WARPS * 32, 0, st>>>(op.ent, op.chunk_row, op.whead, t0, t1, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols, push); break;
+        case 0: launch_k(k_spmv<L, V, 0, HOT, PUSH>, blocks, WARPS * 32, 0, st, op.ent, op.chunk_row, op.whead, t0, t1, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols, push); break;
+        case 8: launch_k(k_spmv<L, V, 8, HOT, PUSH>, blocks, WARPS * 32, 0, st, op.ent, op.chunk_row, op.whead, t0, t1, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols, push); break;
+        default: launch_k(k_spmv<L, V, 2, HOT, PUSH>, blocks, WARPS * 32, 0, st, op.ent, op.chunk_row, op.whead, t0, t1, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols, push); break;
         }
 }
 
@@ -276,7 +278,7 @@ int launch_lv(const SpOp &op, const ModP &m, const u32 *x, u32 *y, const DevSmal
         }
         int64_t threads = (t1 - scan) * L;
         if (threads > 0)
-                k_spmv_fix<L, V><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(op.tail_row, op.span, op.whead, scan, t0, t1, y, m, state,
+                launch_k(k_spmv_fix<L, V>, (unsigned)((threads + 255) / 256), 256, 0, st, op.tail_row, op.span, op.whead, scan, t0, t1, y, m, state,
                                                                                    push ? *push : none);
         return 2;
 }

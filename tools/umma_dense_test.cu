@@ -215,6 +215,19 @@ static int test_ortho(const std::vector<int64_t> &sizes)
                                         printf("    %-36s %.3f ms  (%.0f GB/s of 3 reads + 2 writes)\n", names[which + 1], best, rows * 320.0 / best * 1e-6);
                                 }
                         }
+                        // sustained, as the loop runs it: 40 launches back to back, average (not best-of), separate outputs vs in place
+                        if (pi == 0 && rows >= 1000000) {
+                                for (int inplace = 0; inplace < 2; inplace++) {
+                                        launch_ortho_umma(16, m, rows, v, Av, p, inplace ? v : vo[1], inplace ? p : po[1], mats, nullptr, 1, 0);
+                                        CK(cudaEventRecord(e0));
+                                        for (int rep = 0; rep < 40; rep++)
+                                                launch_ortho_umma(16, m, rows, v, Av, p, inplace ? v : vo[1], inplace ? p : po[1], mats, nullptr, 1, 0);
+                                        CK(cudaEventRecord(e1));
+                                        float ms = time_ms(e0, e1) / 40;
+                                        printf("    default variant, 40 launches back to back, %-16s %.3f ms average  (%.0f GB/s)\n",
+                                               inplace ? "in place:" : "separate outputs:", ms, rows * 320.0 / ms * 1e-6);
+                                }
+                        }
                         // in place, as the iteration calls it (v_out = v, p_out = p)
                         if (pi == 2) {
                                 launch_ortho_umma(16, m, rows, v, Av, p, v, p, mats, nullptr, 1, 0);
