@@ -39,12 +39,18 @@ struct SpOp {
         u32 *tail_row = nullptr;   // [ntiles]    row left open at the end of the tile (started in it)
         u32 *span = nullptr;       // [ntiles]    number of following tiles that finish that row (0: none)
         u32 *whead = nullptr;      // [ntiles*n_pad] scratch: the tile's contribution to a row opened earlier
+        // Look-back completion of rows that cross tile borders (inside k_spmv, no second kernel): the tile in which such a
+        // row ENDS adds up the partial left in y by the tile where it started and the whead of the tiles in between.
+        u32 *back = nullptr;       // [ntiles]    > 0: the row open at the start of this tile ends in it and started `back` tiles earlier
+        u32 *ready = nullptr;      // [ntiles]    flag: the tile's part of the row open at its end is in memory (reset by the finisher)
+        bool lookback = false;     // true (BLK_SPMV_FIX=lookback): finish those rows inside k_spmv; default: k_spmv_fix (faster, measured)
         size_t bytes = 0;
         // Row pieces for pipelining a product with the exchange of its result (multi-GPU): piece q is
         // tiles [piece_tile[q], piece_tile[q+1]); after its fix-up, rows [piece_row[q], piece_row[q+1])
         // are final.  piece_scan[q] <= piece_tile[q] is the first tile whose open row ends in piece q.
         std::vector<int64_t> piece_tile, piece_row, piece_scan;
-        u32 hot_cols = 0;          // > 0: x rows [0, hot_cols) are gathered with L2 evict_last, the rest evict_first
+        u32 hot_cols = 0;          // > 0: entries carry a HOT bit (bit 30 of the column word): those x rows are gathered with
+                                   // L2 evict_last, the rest evict_first (columns are then limited to 2^30)
 };
 
 // n x n working set of one iteration, resident on the device.  All matrices are stored with
@@ -135,16 +141,28 @@ static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 blo
 }
 #endif
 
+// Which x rows of an operator are "hot" (the high-degree prefix of every rank's block of a degree-sorted dimension):
+// column c is hot iff c - off[w] < per, w = the block with off[w] <= c < off[w+1].  per == 0: no hot rows.
+struct HotCols {
+        static constexpr int MAXB = 64;
+        int blocks = 0;
+        u32 per = 0;
+        int64_t off[MAXB + 1] = {0};
+};
+
 // ---- launchers (each returns the number of kernels it launched) ---------------------------
 // layout_build.cu
 std::string build_operator(SpOp *op, const Geometry &geo, int chunk_len, int64_t rows, int64_t cols,
                            int64_t row_lo, int64_t nnz, const int32_t *d_row, const int32_t *d_col,
                            const u32 *d_val, u32 prime, const u32 *row_map, const u32 *col_map, int pieces,
-                           cudaStream_t st);
+                           cudaStream_t st, const HotCols *hot = nullptr);
 void free_operator(SpOp *op);
-// old->new / new->old labels of one dimension sorted by decreasing number of entries
+// old->new / new->old labels of one dimension sorted by decreasing number of entries; world > 1: the sorted
+// sequence is then dealt round-robin to `world` contiguous blocks (position s of the sorted order goes to block
+// s % world, place s / world), so that every block gets the same share of heavy rows -- equal rows, equal
+// non-zeros, and its own hot prefix; block_off[world + 1] receives the block boundaries.
 std::string degree_sort_maps(int64_t nnz, const int32_t *d_idx, int64_t dim, u32 **old2new, u32 **new2old,
-                             cudaStream_t st);
+                             cudaStream_t st, int world = 1, int64_t *block_off = nullptr);
 
 // Peer copies of an output block (multi-GPU, peer-mapped device pointers): y[q] addresses the same
 // row origin on peer q as the local output pointer of the launch, so a finished row r goes to

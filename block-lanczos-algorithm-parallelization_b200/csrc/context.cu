@@ -1240,7 +1240,11 @@ int build_graph(blk_ctx *c)
         return 0;
 }
 
-int kernels_per_iteration(const blk_ctx *c) { return c->fuse_small ? 6 : 7; }
+int kernels_per_iteration(const blk_ctx *c)
+{
+        // two products (+ their k_spmv_fix unless the rows crossing tiles are finished by look-back), dots, [small], orthogonalize
+        return (c->S1.lookback ? 1 : 2) + (c->S2.lookback ? 1 : 2) + 1 + (c->fuse_small ? 0 : 1) + 1;
+}
 
 }  // namespace
 

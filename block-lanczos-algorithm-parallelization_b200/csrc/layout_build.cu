@@ -5,6 +5,8 @@
 // sequential/lanczos_modp.c:277-286); sorting is legal because results are canonical residues
 // and therefore independent of summation order.
 #include <cub/cub.cuh>
+#include <cstdlib>
+#include <cstring>
 #include "blk_internal.cuh"
 
 #define CK(call)                                                                                   \
@@ -59,8 +61,10 @@ __device__ __forceinline__ int64_t interleave(int64_t pos, int G, int Q)
         return t * tile + (int64_t)i * G + g;
 }
 
+// hot (HotCols::per > 0): bit 30 of the column word marks the x rows that belong to the L2-resident hot prefix of
+// their owner's block -- column c is hot iff c - off[w] < per for the block w with off[w] <= c < off[w+1].
 __global__ void k_scatter(int64_t nnz, const u64 *__restrict__ keys, const u32 *__restrict__ vals,
-                          const u32 *__restrict__ empties_before, uint2 *__restrict__ ent, int G, int Q)
+                          const u32 *__restrict__ empties_before, uint2 *__restrict__ ent, int G, int Q, HotCols hot)
 {
         int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
         if (s >= nnz) return;
@@ -68,7 +72,13 @@ __global__ void k_scatter(int64_t nnz, const u64 *__restrict__ keys, const u32 *
         u32 r = (u32)(k >> 32);
         bool last = (s == nnz - 1) || ((u32)(keys[s + 1] >> 32) != r);
         int64_t pos = s + (int64_t)empties_before[r];
-        ent[interleave(pos, G, Q)] = make_uint2((u32)k | (last ? 0x80000000u : 0u), vals[s]);
+        u32 c = (u32)k, flag = 0;
+        if (hot.per) {
+                int w = 0;
+                while (w + 1 < hot.blocks && (int64_t)c >= hot.off[w + 1]) w++;
+                if ((int64_t)c - hot.off[w] < (int64_t)hot.per) flag = 0x40000000u;
+        }
+        ent[interleave(pos, G, Q)] = make_uint2(c | flag | (last ? 0x80000000u : 0u), vals[s]);
 }
 
 __global__ void k_dummies(int64_t rows, const u32 *__restrict__ cnt, const u64 *__restrict__ rowptr,
@@ -105,7 +115,7 @@ __global__ void k_chunk_rows(int64_t nchunks, int Q, int64_t stored, int64_t row
 
 __global__ void k_tile_tails(int64_t ntiles, int64_t tile, int64_t stored, int64_t rows,
                              const u64 *__restrict__ rowptr, u32 *__restrict__ tail_row,
-                             u32 *__restrict__ span)
+                             u32 *__restrict__ span, u32 *__restrict__ back)
 {
         int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
         if (t >= ntiles) return;
@@ -121,6 +131,7 @@ __global__ void k_tile_tails(int64_t ntiles, int64_t tile, int64_t stored, int64
         }
         tail_row[t] = tr;
         span[t] = sp;
+        if (sp) back[t + sp] = sp;          // (a tile finishes at most one such row: the one open at its start)
 }
 
 }  // namespace
@@ -128,7 +139,7 @@ __global__ void k_tile_tails(int64_t ntiles, int64_t tile, int64_t stored, int64
 void free_operator(SpOp *op)
 {
         cudaFree(op->ent); cudaFree(op->chunk_row); cudaFree(op->tail_row);
-        cudaFree(op->span); cudaFree(op->whead);
+        cudaFree(op->span); cudaFree(op->whead); cudaFree(op->back); cudaFree(op->ready);
         *op = SpOp();
 }
 
@@ -147,7 +158,7 @@ static int pick_chunk_len(int64_t stored, int G)
 std::string build_operator(SpOp *op, const Geometry &geo, int chunk_len, int64_t rows, int64_t cols,
                            int64_t row_lo, int64_t nnz, const int32_t *d_row, const int32_t *d_col,
                            const u32 *d_val, u32 prime, const u32 *row_map, const u32 *col_map, int pieces,
-                           cudaStream_t st)
+                           cudaStream_t st, const HotCols *hot)
 {
         *op = SpOp();
         op->rows = rows; op->cols = cols; op->nnz = nnz; op->G = geo.G;
@@ -251,11 +262,24 @@ std::string build_operator(SpOp *op, const Geometry &geo, int chunk_len, int64_t
         CKC(cudaMalloc(&op->tail_row, sizeof(u32) * (size_t)op->ntiles));
         CKC(cudaMalloc(&op->span, sizeof(u32) * (size_t)op->ntiles));
         CKC(cudaMalloc(&op->whead, sizeof(u32) * (size_t)op->ntiles * geo.np));
-        op->bytes = ent_b + sizeof(u32) * (size_t)(nchunks + 2 * op->ntiles + op->ntiles * geo.np);
+        CKC(cudaMalloc(&op->back, sizeof(u32) * (size_t)op->ntiles));
+        CKC(cudaMalloc(&op->ready, sizeof(u32) * (size_t)op->ntiles));
+        CKC(cudaMemsetAsync(op->back, 0, sizeof(u32) * (size_t)op->ntiles, st));
+        CKC(cudaMemsetAsync(op->ready, 0, sizeof(u32) * (size_t)op->ntiles, st));
+        {
+                // measured (profiles/r02_spmv_lookback.txt): look-back costs every warp a fence and two more
+                // dependent L2 round trips -- slower than the separate fix-up kernel on every configuration, so it is
+                // an opt-in (BLK_SPMV_FIX=lookback)
+                const char *e = getenv("BLK_SPMV_FIX");
+                op->lookback = e && !strcmp(e, "lookback");
+        }
+        op->bytes = ent_b + sizeof(u32) * (size_t)(nchunks + 4 * op->ntiles + op->ntiles * geo.np);
         CKC(cudaMemsetAsync(op->ent, 0, ent_b, st));
         CKC(cudaMemsetAsync(op->whead, 0, sizeof(u32) * (size_t)op->ntiles * geo.np, st));
         if (nnz > 0) {
-                k_scatter<<<nblk(nnz), TB, 0, st>>>(nnz, dk.Current(), dv.Current(), empty, op->ent, op->G, op->Q);
+                HotCols h;
+                if (hot && hot->per > 0 && cols < (1ll << 30)) { h = *hot; op->hot_cols = h.per; }
+                k_scatter<<<nblk(nnz), TB, 0, st>>>(nnz, dk.Current(), dv.Current(), empty, op->ent, op->G, op->Q, h);
                 CKC(cudaGetLastError());
         }
         k_dummies<<<nblk(rows), TB, 0, st>>>(rows, cnt, rowptr, op->ent, op->G, op->Q);
@@ -263,7 +287,7 @@ std::string build_operator(SpOp *op, const Geometry &geo, int chunk_len, int64_t
         k_chunk_rows<<<nblk(nchunks), TB, 0, st>>>(nchunks, op->Q, op->stored, rows, rowptr, op->chunk_row);
         CKC(cudaGetLastError());
         k_tile_tails<<<nblk(op->ntiles), TB, 0, st>>>(op->ntiles, tile, op->stored, rows, rowptr,
-                                                      op->tail_row, op->span);
+                                                      op->tail_row, op->span, op->back);
         CKC(cudaGetLastError());
         CKC(cudaStreamSynchronize(st));
 
@@ -323,10 +347,24 @@ __global__ void k_invert_perm(int64_t dim, const u32 *__restrict__ new2old, u32 
         if (s >= dim) return;
         old2new[new2old[s]] = (u32)s;
 }
+// sorted position s -> label of block s % W, place s / W; block w starts at off[w] = sum_{q<w} ceil((dim - q) / W)
+__global__ void k_deal_labels(int64_t dim, int W, const u32 *__restrict__ sorted2old, u32 *__restrict__ new2old,
+                              u32 *__restrict__ old2new)
+{
+        int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (s >= dim) return;
+        const int w = (int)(s % W);
+        // off[w] = sum_{q<w} ceil((dim - q)/W) = w * floor(dim / W) + min(w, dim % W)
+        const int64_t off = (int64_t)w * (dim / W) + (w < dim % W ? w : dim % W);
+        const u32 lab = (u32)(off + s / W);
+        const u32 old = sorted2old[s];
+        new2old[lab] = old;
+        old2new[old] = lab;
+}
 }  // namespace
 
 std::string degree_sort_maps(int64_t nnz, const int32_t *d_idx, int64_t dim, u32 **old2new, u32 **new2old,
-                             cudaStream_t st)
+                             cudaStream_t st, int world, int64_t *block_off)
 {
         *old2new = *new2old = nullptr;
         u32 *cnt = nullptr, *key[2] = {nullptr, nullptr}, *val[2] = {nullptr, nullptr};
@@ -355,8 +393,15 @@ std::string degree_sort_maps(int64_t nnz, const int32_t *d_idx, int64_t dim, u32
         CKD(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, dim, 0, 32, st));
         CKD(cudaMalloc(&tmp, tb ? tb : 16));
         CKD(cub::DeviceRadixSort::SortPairs(tmp, tb, dk, dv, dim, 0, 32, st));
-        CKD(cudaMemcpyAsync(*new2old, dv.Current(), b, cudaMemcpyDeviceToDevice, st));
-        k_invert_perm<<<nblk(dim), TB, 0, st>>>(dim, *new2old, *old2new);
+        if (world > 1) {
+                k_deal_labels<<<nblk(dim), TB, 0, st>>>(dim, world, dv.Current(), *new2old, *old2new);
+                for (int w = 0; w <= world && block_off; w++)
+                        block_off[w] = w == world ? dim : (int64_t)w * (dim / world) + (w < dim % world ? w : dim % world);
+        } else {
+                CKD(cudaMemcpyAsync(*new2old, dv.Current(), b, cudaMemcpyDeviceToDevice, st));
+                k_invert_perm<<<nblk(dim), TB, 0, st>>>(dim, *new2old, *old2new);
+                if (block_off) { block_off[0] = 0; block_off[1] = dim; }
+        }
         CKD(cudaGetLastError());
         CKD(cudaStreamSynchronize(st));
         cleanup();

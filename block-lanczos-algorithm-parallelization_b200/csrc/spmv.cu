@@ -74,11 +74,19 @@ template <int V> __device__ __forceinline__ void load_vec_cg(u32 (&o)[V], const 
         for (int k = 0; k < V; k++) o[k] = w[k];
 }
 
+__device__ __forceinline__ u32 ld_acquire(const u32 *p)
+{
+        u32 v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+        return v;
+}
+
+// back / ready (nullable together): complete the rows that cross tile borders by look-back (see SpOp)
 template <int L, int V, int FOLD, int HOT, int PUSH>
 __global__ void __launch_bounds__(WARPS * 32)
 k_spmv(const uint2 *__restrict__ ent, const u32 *__restrict__ chunk_row, u32 *__restrict__ whead,
        int64_t tile0, int64_t ntiles, int Q, u32 rows, const u32 *__restrict__ x, u32 *__restrict__ y, ModP m,
-       const DevSmall *__restrict__ state, u32 hot, PushTargets push)
+       const DevSmall *__restrict__ state, u32 hot, PushTargets push, const u32 *__restrict__ back, u32 *__restrict__ ready)
 {
         pdl_prologue();
         u64 pol_hot = 0, pol_cold = 0;
@@ -117,8 +125,9 @@ k_spmv(const uint2 *__restrict__ ent, const u32 *__restrict__ chunk_row, u32 *__
 #pragma unroll
                 for (int u = 0; u < U; u++)
                 {
-                        const u32 col = ee[u].x & 0x7fffffffu;
-                        load_vec<V, HOT>(xv[u], xs + (size_t)col * NP, col < hot ? pol_hot : pol_cold);
+                        // (HOT: bit 30 of the column word, set at layout-build time, marks the L2-resident x rows)
+                        const u32 col = ee[u].x & (HOT ? 0x3fffffffu : 0x7fffffffu);
+                        load_vec<V, HOT>(xv[u], xs + (size_t)col * NP, (ee[u].x & 0x40000000u) ? pol_hot : pol_cold);
                 }
 #pragma unroll
                 for (int u = 0; u < U; u++) {
@@ -191,6 +200,60 @@ k_spmv(const uint2 *__restrict__ ent, const u32 *__restrict__ chunk_row, u32 *__
         }
         if (g == 0 && head_type != 0) store_vec<V>(whead + t * NP + sub * V, headv);
 
+        if (back) {
+                // ---- rows that cross tile borders, finished here instead of by a second kernel.
+                // (1) A row still open at the END of this tile needs this tile's part later: it is in memory now
+                //     (the partial row in y if the row started here, whead[t] if the whole tile lies inside it).
+                const int open_end = __shfl_sync(0xffffffffu, (int)(pending && (head_type == 2 || has_tail)), 31);
+                __syncwarp();
+                if (open_end && lane == 0) {
+                        __threadfence();
+                        *(volatile u32 *)(ready + t) = 1u;
+                }
+                // (2) The row open at the START of this tile ends in it and started bk tiles back: wait for those
+                //     tiles (they have lower indices, so they are running or done), add the partial of the first, the
+                //     whead of the ones in between and this tile's own head, and store the finished row.
+                const u32 bk = __ldg(back + t);
+                if (bk) {
+                        for (u32 j = 1 + lane; j <= bk; j += 32)
+                                while (ld_acquire(ready + (t - j)) == 0) { }
+                        __syncwarp();
+                        const u32 hrow = __shfl_sync(0xffffffffu, cr & 0x7fffffffu, 0);      // group 0 started on that row
+                        u64 sum[V];
+#pragma unroll
+                        for (int k = 0; k < V; k++) sum[k] = 0;
+                        for (u32 j = 1 + g; j < bk; j += G) {
+                                u32 h[V];
+                                load_vec_cg<V>(h, whead + (size_t)(t - j) * NP + sub * V);
+#pragma unroll
+                                for (int k = 0; k < V; k++) sum[k] += h[k];
+                        }
+                        if (g == 0) {
+                                u32 h[V];
+                                load_vec_cg<V>(h, ys + (size_t)hrow * NP);
+#pragma unroll
+                                for (int k = 0; k < V; k++) sum[k] += (u64)h[k] + headv[k];
+                        }
+#pragma unroll
+                        for (int d = L; d < 32; d <<= 1) {
+#pragma unroll
+                                for (int k = 0; k < V; k++) sum[k] += __shfl_xor_sync(0xffffffffu, sum[k], d);
+                        }
+                        if (g == 0) {
+                                u32 o[V];
+#pragma unroll
+                                for (int k = 0; k < V; k++) o[k] = mp_reduce(sum[k], m);
+                                store_vec<V>(ys + (size_t)hrow * NP, o);
+                                if (PUSH) {
+#pragma unroll
+                                        for (int q = 0; q < PushTargets::MAX; q++)
+                                                if (q < push.n) store_vec<V>(push.y[q] + (size_t)hrow * NP + sub * V, o);
+                                }
+                        }
+                        for (u32 j = 1 + lane; j <= bk; j += 32) ready[t - j] = 0u;          // consumed: re-arm for the next launch
+                }
+        }
+
         if (PUSH) {
                 // Rows this warp has finalised: every row that STARTS in the tile, except the one still open at
                 // its end (that one is finished -- and pushed -- by k_spmv_fix).  They are consecutive:
@@ -253,10 +316,12 @@ void launch_hot(const SpOp &op, const ModP &m, const u32 *x, u32 *y, const DevSm
 {
         unsigned blocks = (unsigned)((t1 - t0 + WARPS - 1) / WARPS);
         if (blocks == 0) return;
+        const u32 *back = op.lookback ? op.back : nullptr;
+        u32 *ready = op.lookback ? op.ready : nullptr;
         switch (m.fold_every) {
-        case 0: launch_k(k_spmv<L, V, 0, HOT, PUSH>, blocks, WARPS * 32, 0, st, op.ent, op.chunk_row, op.whead, t0, t1, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols, push); break;
-        case 8: launch_k(k_spmv<L, V, 8, HOT, PUSH>, blocks, WARPS * 32, 0, st, op.ent, op.chunk_row, op.whead, t0, t1, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols, push); break;
-        default: launch_k(k_spmv<L, V, 2, HOT, PUSH>, blocks, WARPS * 32, 0, st, op.ent, op.chunk_row, op.whead, t0, t1, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols, push); break;
+        case 0: launch_k(k_spmv<L, V, 0, HOT, PUSH>, blocks, WARPS * 32, 0, st, op.ent, op.chunk_row, op.whead, t0, t1, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols, push, back, ready); break;
+        case 8: launch_k(k_spmv<L, V, 8, HOT, PUSH>, blocks, WARPS * 32, 0, st, op.ent, op.chunk_row, op.whead, t0, t1, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols, push, back, ready); break;
+        default: launch_k(k_spmv<L, V, 2, HOT, PUSH>, blocks, WARPS * 32, 0, st, op.ent, op.chunk_row, op.whead, t0, t1, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols, push, back, ready); break;
         }
 }
 
@@ -276,6 +341,7 @@ int launch_lv(const SpOp &op, const ModP &m, const u32 *x, u32 *y, const DevSmal
                 if (hot) launch_hot<L, V, 1, 0>(op, m, x, y, state, st, t0, t1, none);
                 else launch_hot<L, V, 0, 0>(op, m, x, y, state, st, t0, t1, none);
         }
+        if (op.lookback) return 1;                     // rows crossing tile borders were finished inside k_spmv
         int64_t threads = (t1 - scan) * L;
         if (threads > 0)
                 launch_k(k_spmv_fix<L, V>, (unsigned)((threads + 255) / 256), 256, 0, st, op.tail_row, op.span, op.whead, scan, t0, t1, y, m, state,

@@ -8,7 +8,11 @@ the kernels; this file is the specification they implement, small enough to read
     chunk's first entry, plus HEAD_OPEN when that row started in an earlier chunk;
   * a group stores the rows that start AND end inside its chunk; the piece of a row it inherits (head) and the row
     it leaves unfinished (tail) are stitched inside the warp by a suffix scan over the groups; what crosses tile
-    borders goes through whead[tile] and is finished by k_spmv_fix using tail_row[tile] and span[tile].
+    borders goes through whead[tile] and is finished either by k_spmv_fix using tail_row[tile] and span[tile]
+    (BLK_SPMV_FIX=kernel), or -- the default -- inside k_spmv by look-back: the tile in which the row ENDS
+    (back[tile] = number of tiles back to the one where it started) waits for the `ready` flags of those tiles,
+    adds the partial row the first one left in y, the whead of the ones in between and its own head, and clears
+    the flags again.
 """
 import numpy as np
 import pytest
@@ -71,12 +75,19 @@ class ChunkStream:
         idx = np.arange(self.ntiles * G * Q).reshape(self.ntiles, G, Q)          # [tile][chunk][i] -> stream position
         return idx.transpose(0, 2, 1).reshape(-1)                                # position in memory -> stream position
 
-    def spmv(self, xblk, n, p):
-        """y <- S x exactly as the two kernels do it (python integers: no overflow questions here)"""
+    def spmv(self, xblk, n, p, lookback=False):
+        """y <- S x exactly as the kernels do it (python integers: no overflow questions here)"""
         Q, G = self.Q, self.G
+        back = np.zeros(self.ntiles, np.int64)                   # layout_build.cu k_tile_tails: back[t + span] = span
+        for t in range(self.ntiles):
+            if self.span[t]:
+                assert back[t + self.span[t]] == 0               # a tile finishes at most one row
+                back[t + self.span[t]] = self.span[t]
+        ready = np.zeros(self.ntiles, bool)
         X = xblk.reshape(self.cols, n).astype(object)
         y = np.zeros((self.rows + 1, n), dtype=object)           # row `rows` = the padding's sink, never read
         whead = np.zeros((self.ntiles, n), dtype=object)
+        pending_last = np.zeros(self.ntiles, bool)               # k_spmv: pending && (head_type == 2 || has_tail) of the last group
         for t in range(self.ntiles):                              # ---- k_spmv: one warp per tile
             headv = np.zeros((G, n), dtype=object)
             head_type = np.zeros(G, int)
@@ -104,6 +115,8 @@ class ChunkStream:
                         headv[g], head_type[g] = acc % p, 2       # the whole chunk lies inside one row
                     elif row < self.rows:
                         tailv[g], has_tail[g], tail_row[g] = acc % p, True, row
+                    if g == G - 1:
+                        pending_last[t] = head_type[g] == 2 or has_tail[g]
             # suffix scan: S_g = heads of chunks g, g+1, ... up to the chunk in which the row ends
             S = headv.copy()
             closed = head_type != 2
@@ -116,6 +129,21 @@ class ChunkStream:
                     y[tail_row[g]] = (tailv[g] + (S[g + 1] if g < G - 1 else 0)) % p
             if head_type[0] != 0:
                 whead[t] = S[0]
+            if lookback:
+                # (1) the row open at the end of the tile: its part is in memory now
+                if pending_last[t] :
+                    ready[t] = True
+                # (2) the row open at the start ends here and began back[t] tiles earlier (lower tiles: already done)
+                bk = int(back[t])
+                if bk:
+                    assert self.head_open[t * G] and closed[0] and all(ready[t - j] for j in range(1, bk + 1))
+                    hrow = int(self.chunk_row[t * G])
+                    y[hrow] = (y[hrow] + sum(whead[t - j] for j in range(1, bk)) + S[0]) % p
+                    for j in range(1, bk + 1):
+                        ready[t - j] = False
+        if lookback:
+            assert not ready.any()                                # every flag was consumed and cleared: re-armed for the next launch
+            return np.array(y[:self.rows].tolist(), dtype=np.uint32).ravel()
         for t in range(self.ntiles):                              # ---- k_spmv_fix: rows crossing tile borders
             if self.span[t]:
                 y[self.tail_row[t]] = (y[self.tail_row[t]] + sum(whead[t + 1 + j] for j in range(int(self.span[t])))) % p
@@ -150,6 +178,7 @@ def test_chunk_stream_model_matches_oracle(lib, oracle, Q, G):
             x[::3] = p - 1
             want = oracle.sparse_matrix_vector_product(Mp, x, transpose, n, p)
             assert np.array_equal(cs.spmv(x, n, p), want), (name, transpose)
+            assert np.array_equal(cs.spmv(x, n, p, lookback=True), want), (name, transpose, "look-back")
             # layout invariants: every row owns >= 1 stored entry, exactly one LAST per row, padding after the data
             assert cs.stored == Mp.nnz + int((np.bincount((Mp.j if transpose else Mp.i), minlength=cs.rows) == 0).sum())
             assert int(cs.last.sum()) == cs.rows and not cs.last[cs.stored:].any()

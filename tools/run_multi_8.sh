@@ -1,32 +1,38 @@
 #!/bin/bash
-# 8-GPU measurement call (round 2): exchange-mode A/B on config 4 through bench.py (one process per GPU, the
-# driver's launch), a subset of the multi-GPU parity tests, then the full bench line.
+# Multi-GPU measurement call (round 2), sized for a slot that is charged G times its wall time:
+#   1. exchange-mode A/B on a config-4-sized matrix with tools/mg_check (one process, one thread per GPU: starts in seconds)
+#   2. a few parity checks at G GPUs (group context, P x Q grid, CLI, one torchrun run = CUDA-IPC path)
+#   3. the bench line as the driver launches it (torchrun, one process per GPU)
 mkdir -p gpurun_out
 G=${1:-8}
+L=gpurun_out/r2_f_mgtime${G}.log
+: > $L
 nvidia-smi topo -m > gpurun_out/r2_f_topo.txt 2>&1
-run() {   # name, env...
+SIZE="50000000 50000000 1473000000 16 2147483647 10"
+ab() {   # name, env...
   name=$1; shift
-  env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port $((29600 + RANDOM % 300)) \
-      bench.py --gpus $G --steps 10 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/r2_f_ab_${name}.json 2> gpurun_out/r2_f_ab_${name}.err
-  python - "$name" <<'PY'
-import json, sys
-name = sys.argv[1]
-try:
-    d = json.loads(open(f"gpurun_out/r2_f_ab_{name}.json").read().strip().splitlines()[-1])
-    ph = {k: round(v, 2) for k, v in d["phases_ms_per_step"].items()}
-    print(f"{name:14s} {d['value']:7.2f} it/s  {d['ms_per_step']:6.2f} ms  e2e {d['e2e']['value']:6.2f}  {ph}  sha {d['state_sha256'][:12]}")
-except Exception as e:
-    print(name, "FAILED", e)
-PY
+  echo "== $name ($*)" >> $L
+  env "$@" timeout 150 tools/mg_check time $G $SIZE 2>&1 | grep -v "^NCCL version" >> $L
 }
-run push
-run nccl BLK_EXCHANGE=nccl
-run pushk BLK_PUSH_AV=kernel
-run push_p8 BLK_PIECES=8
-run push_c16 BLK_PUSH_CTAS=16
-run push_c64 BLK_PUSH_CTAS=64
-run pushk_p8 BLK_PUSH_AV=kernel BLK_PIECES=8
-timeout 600 python -m pytest tests/test_gpu_multi.py -q --timeout=240 -x \
-  -k "(group_context and (8-push or 8-nccl or 4-pieces8)) or (sharded and 8) or (block_grid and (4x2 or 2x2)) or (arrival and 4-3) or cli_on_several" \
-  > gpurun_out/r2_f_pytest8.log 2>&1
-tail -4 gpurun_out/r2_f_pytest8.log
+ab push BLK_EXCHANGE=push
+ab nccl BLK_EXCHANGE=nccl
+ab pushk BLK_EXCHANGE=push BLK_PUSH_AV=kernel
+ab push_p8 BLK_EXCHANGE=push BLK_PIECES=8
+ab push_p2 BLK_EXCHANGE=push BLK_PIECES=2
+ab push_c16 BLK_EXCHANGE=push BLK_PUSH_CTAS=16
+ab push_c64 BLK_EXCHANGE=push BLK_PUSH_CTAS=64
+ab grid BLK_EXPERIMENTAL=1 BLK_GRID=auto
+ab colblocks4 BLK_EXPERIMENTAL=1 BLK_COLBLOCKS=4
+cat $L
+# parity at G GPUs
+echo "== parity" >> $L
+BLK_EXPERIMENTAL=1 BLK_GRID=auto timeout 120 tools/mg_check check $G 2>&1 | tail -7 >> $L
+timeout 120 tools/mg_check check $G 2>&1 | tail -7 >> $L
+timeout 400 python -m pytest tests/test_gpu_multi.py -q --timeout=200 -x \
+  -k "(group_context and ${G}-push) or (sharded and ${G}) or cli_on_several" > gpurun_out/r2_f_pytest${G}.log 2>&1
+tail -4 gpurun_out/r2_f_pytest${G}.log
+tail -16 $L
+# the driver's launch
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29711 \
+    bench.py --gpus $G --steps 10 --warmup 3 > gpurun_out/r2_f_bench${G}.json 2> gpurun_out/r2_f_bench${G}.err
+tail -c 1500 gpurun_out/r2_f_bench${G}.json
