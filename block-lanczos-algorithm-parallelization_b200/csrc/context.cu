@@ -206,6 +206,12 @@ struct blk_ctx {
         int64_t launches = 0;
         size_t block_bytes = 0;
 
+        // With relabelled rows on several GPUs a rank's rows are scattered over the caller's (host-order) blocks, so
+        // host <-> device copies are split by HOST rows instead: rank r moves host rows [h0, h1) over PCIe and the
+        // rows find their owners (or their readers) over NVLink.
+        bool relabel_mg() const { return n_old2new != nullptr && world > 1; }
+        int64_t h0() const { return relabel_mg() ? N * rank / world : n_off[rank]; }
+        int64_t h1() const { return relabel_mg() ? N * (rank + 1) / world : n_off[rank + 1]; }
         int64_t n0() const { return n_off[rank]; }
         int64_t n1() const { return n_off[rank + 1]; }
         int64_t m0() const { return m_off[rank]; }
@@ -315,25 +321,34 @@ bool equal_blocks(const std::vector<int64_t> &off)
         return true;
 }
 
-__global__ void k_count_rows(int64_t nnz, const int32_t *__restrict__ idx, int64_t dim, u32 *__restrict__ cnt)
+// `map` (nullable): count under the relabelled index map[idx]
+__global__ void k_count_rows(int64_t nnz, const int32_t *__restrict__ idx, int64_t dim, u32 *__restrict__ cnt,
+                             const u32 *__restrict__ map)
 {
         int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
         if (s >= nnz) return;
         int64_t r = idx[s];
-        if (r >= 0 && r < dim) atomicAdd(&cnt[r], 1u);
+        if (r < 0 || r >= dim) return;
+        if (map) r = map[r];
+        atomicAdd(&cnt[r], 1u);
 }
 
+// entries whose (relabelled) key lies in [lo, hi); key_map / other_map (nullable, key_dim / other_dim entries): the
+// relabelling of the two index spaces, applied here so that the layout builder sees final labels
 __global__ void k_select_range(int64_t nnz, const int32_t *__restrict__ key, const int32_t *__restrict__ other,
                                const u32 *__restrict__ val, int64_t lo, int64_t hi, int32_t *__restrict__ okey,
                                int32_t *__restrict__ oother, u32 *__restrict__ oval,
-                               unsigned long long *__restrict__ counter)
+                               unsigned long long *__restrict__ counter, const u32 *__restrict__ key_map, int64_t key_dim,
+                               const u32 *__restrict__ other_map, int64_t other_dim)
 {
         int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
         if (s >= nnz) return;
-        int64_t k = key[s];
+        int64_t k = key[s], o = other[s];
+        if (key_map) { if (k < 0 || k >= key_dim) return; k = key_map[k]; }
         if (k < lo || k >= hi) return;
+        if (other_map && o >= 0 && o < other_dim) o = other_map[o];
         unsigned long long pos = atomicAdd(counter, 1ull);
-        okey[pos] = (int32_t)k; oother[pos] = other[s]; oval[pos] = val[s];
+        okey[pos] = (int32_t)k; oother[pos] = (int32_t)o; oval[pos] = val[s];
 }
 
 inline unsigned nb(int64_t n) { return (unsigned)((n + 255) / 256); }
@@ -1277,13 +1292,13 @@ bool env_flag(const char *name)
 }
 
 // entries per row of one dimension (host copy)
-int count_dimension(blk_ctx *c, int64_t nnz, const int32_t *idx, int64_t dim, std::vector<u32> *out)
+int count_dimension(blk_ctx *c, int64_t nnz, const int32_t *idx, int64_t dim, std::vector<u32> *out, const u32 *map = nullptr)
 {
         Scratch tmp;
         u32 *dc = nullptr;
         if (tmp.alloc(&dc, sizeof(u32) * (size_t)dim)) return 1;
         CU(cudaMemsetAsync(dc, 0, sizeof(u32) * (size_t)dim, c->stream));
-        if (nnz) k_count_rows<<<nb(nnz), 256, 0, c->stream>>>(nnz, idx, dim, dc);
+        if (nnz) k_count_rows<<<nb(nnz), 256, 0, c->stream>>>(nnz, idx, dim, dc, map);
         out->assign((size_t)dim, 0);
         if (dim) CU(cudaMemcpyAsync(out->data(), dc, sizeof(u32) * (size_t)dim, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
@@ -1568,19 +1583,30 @@ int create_impl(blk_ctx *c, const blk_params *prm)
                 }
         }
 
-        // ---- degree-sorted labels for the N dimension + L2-resident hot prefix (single GPU)
+        // ---- degree-sorted labels for the N dimension + L2-resident hot prefix.  The rows of the Lanczos vectors can
+        // be stored under any labels (dots are order-free, orthogonalize is row-wise); sorting them by decreasing
+        // number of entries makes the rows product 1 gathers most often a contiguous prefix that L2 can keep.  With
+        // several GPUs the sorted sequence is dealt round-robin to the ranks' blocks: every rank owns the same
+        // number of rows and of non-zeros (to within one giant row) and its own share of the hot rows.
+        HotCols hot;
         {
                 const char *e = getenv("BLK_HOT"), *emin = getenv("BLK_HOT_MIN_BYTES"), *eb = getenv("BLK_HOT_BYTES");
                 cudaDeviceProp prop;
                 CU(cudaGetDeviceProperties(&prop, c->device));
                 long long min_bytes = emin ? atoll(emin) : 96ll << 20;
                 long long hot_bytes = eb ? atoll(eb) : 24ll << 20;
-                bool on = world == 1 && !c->colblocks && !(e && e[0] == '0') && np >= 4 && nnz > 0 &&
-                          (long long)c->N * np * 4 > min_bytes && hot_bytes > 0;
+                bool on = !c->colblocks && !grid_req && !(e && e[0] == '0') && np >= 4 && nnz > 0 && world <= HotCols::MAXB &&
+                          c->N < (1ll << 30) && (long long)c->N * np * 4 > min_bytes && hot_bytes > 0;
+                if (world > 1 && env_flag("BLK_HOT_SINGLE_ONLY")) on = false;       // A/B switch: round-1 behaviour
                 if (on) {
-                        std::string err = degree_sort_maps(nnz, idxN, c->N, &c->n_old2new, &c->n_new2old, c->stream);
+                        std::vector<int64_t> off((size_t)world + 1, 0);
+                        std::string err = degree_sort_maps(nnz, idxN, c->N, &c->n_old2new, &c->n_new2old, c->stream, world, off.data());
                         if (!err.empty()) return fail(err);
                         c->hot_rows = std::min<int64_t>(c->N, hot_bytes / (4 * np));
+                        hot.blocks = world;
+                        hot.per = (u32)((c->hot_rows + world - 1) / world);
+                        for (int w = 0; w <= world; w++) hot.off[w] = off[(size_t)w];
+                        if (world > 1) c->n_off = off;          // the dealt blocks replace the weight-balanced partition
                         // B200's L2 is two halves (one per die) and lines gathered by SMs of both dies live
                         // in both, so the set-aside has to hold the hot prefix twice.  (A device-wide limit: the
                         // one piece of process state this library changes; restored by blk_destroy.)
@@ -1614,8 +1640,8 @@ int create_impl(blk_ctx *c, const blk_params *prm)
                 std::string err;
                 if (world == 1) {
                         err = build_operator(op, c->geo, prm->chunk_len, hi - lo, cols, lo, nnz, rk, ck, dx, m.p,
-                                             which ? c->n_old2new : nullptr, which ? nullptr : c->n_old2new, 1, c->stream);
-                        if (!which) op->hot_cols = (u32)c->hot_rows;
+                                             which ? c->n_old2new : nullptr, which ? nullptr : c->n_old2new, 1, c->stream,
+                                             which ? nullptr : &hot);
                         if (err.empty() && c->colblocks &&
                             build_colops(c, which ? &c->cb2 : &c->cb1, c->colblocks, prm->chunk_len, nnz, rk, ck, dx, lo, hi, cols,
                                          which ? c->m_off : c->n_off))
@@ -1625,8 +1651,10 @@ int create_impl(blk_ctx *c, const blk_params *prm)
                         int32_t *sr = nullptr, *sc = nullptr; u32 *sx = nullptr;
                         unsigned long long *cnt = nullptr, hcnt = 0;
                         // upper bound of the selection is not known: count first
+                        // (the N dimension may be relabelled: S2 selects its rows, S1 gathers its columns, under the new labels)
+                        const u32 *key_map = which ? c->n_old2new : nullptr, *other_map = which ? nullptr : c->n_old2new;
                         std::vector<u32> hc;
-                        if (count_dimension(c, nnz, rk, which ? c->N : c->Mc, &hc)) return 1;
+                        if (count_dimension(c, nnz, rk, which ? c->N : c->Mc, &hc, key_map)) return 1;
                         int64_t sel = 0;
                         for (int64_t r = lo; r < hi; r++) sel += hc[(size_t)r];
                         std::vector<u32>().swap(hc);
@@ -1634,12 +1662,14 @@ int create_impl(blk_ctx *c, const blk_params *prm)
                             sel_buf.alloc(&sc, sizeof(int32_t) * (size_t)sel) || sel_buf.alloc(&sx, sizeof(u32) * (size_t)sel))
                                 return 1;
                         CU(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
-                        if (nnz) k_select_range<<<nb(nnz), 256, 0, c->stream>>>(nnz, rk, ck, dx, lo, hi, sr, sc, sx, cnt);
+                        if (nnz)
+                                k_select_range<<<nb(nnz), 256, 0, c->stream>>>(nnz, rk, ck, dx, lo, hi, sr, sc, sx, cnt, key_map,
+                                                                               which ? c->N : c->Mc, other_map, which ? c->Mc : c->N);
                         CU(cudaMemcpyAsync(&hcnt, cnt, sizeof(hcnt), cudaMemcpyDeviceToHost, c->stream));
                         CU(cudaStreamSynchronize(c->stream));
                         if ((int64_t)hcnt != sel) err = "shard selection count mismatch";
                         else err = build_operator(op, c->geo, prm->chunk_len, hi - lo, cols, lo, sel, sr, sc, sx, m.p, nullptr, nullptr,
-                                                       want_pieces, c->stream);
+                                                       want_pieces, c->stream, which ? nullptr : &hot);
                         if (err.empty() && c->colblocks &&
                             build_colops(c, which ? &c->cb2 : &c->cb1, c->colblocks, prm->chunk_len, sel, sr, sc, sx, lo, hi, cols,
                                          which ? c->m_off : c->n_off))
@@ -1929,31 +1959,42 @@ int blk_set_state(blk_ctx *c, const uint32_t *v, const uint32_t *p, int32_t n_it
         if (c->is_group()) return group_run(c, [&](blk_ctx *mem, int) { return blk_set_state(mem, v, p, n_iterations); });
         CU(cudaSetDevice(c->device));
         const int np = c->geo.np, n = c->geo.n;
-        // Every rank reads only ITS rows of the host blocks (1/world of the PCIe traffic); the rest of v arrives
-        // from the peers over NVLink.  (The relabelling map exists only when world == 1: all rows are local.)
+        // Every rank reads only ITS share of the host blocks (1/world of the PCIe traffic); the rest of v arrives
+        // from the peers over NVLink.
         const int64_t n0 = c->n0(), ln = c->n1() - n0;
-        if (upload_rows(c, c->n_old2new ? c->v : c->v + (size_t)n0 * np, v + (size_t)n0 * n, ln, c->n_old2new, n0)) return 1;
-        if (c->world > 1 && allgather_rows(c, c->v, c->n_off)) return 1;
-        if (p) {
-                if (upload_rows(c, c->p, p + (size_t)n0 * n, ln, c->n_old2new, n0)) return 1;
-        } else {
-                CU(cudaMemsetAsync(c->p, 0, sizeof(u32) * (size_t)(ln > 0 ? ln : 1) * np, c->stream));
-        }
-        CU(cudaMemsetAsync(c->tmp, 0, sizeof(u32) * (size_t)c->Mc * np, c->stream));
-        if (c->Av_full) CU(cudaMemsetAsync(c->Av_full, 0, sizeof(u32) * (size_t)gather_cap(c->n_off) * np, c->stream));
-        else CU(cudaMemsetAsync(c->Av, 0, sizeof(u32) * (size_t)(ln > 0 ? ln : 1) * np, c->stream));
-        if (c->mg_recur) {
-                // invariant of the multi-GPU loop: tmp = S1 v (gathered), Tp = S1 p (local rows)
-                u32 *pfull = nullptr;
+        const size_t full_rows = (size_t)gather_cap(c->n_off);
+        u32 *pfull = nullptr;                      // p under device labels, all rows (only where it is needed)
+        struct Free { u32 *&q; ~Free() { cudaFree(q); } } free_pfull{pfull};
+        if (c->relabel_mg()) {
+                // host rows [h0, h1) scattered to their labels; exactly one rank contributes each element, so a
+                // sum over the ranks assembles the block
+                const int64_t h0 = c->h0(), hl = c->h1() - h0;
+                CU(cudaMemsetAsync(c->v, 0, sizeof(u32) * full_rows * np, c->stream));
+                if (upload_rows(c, c->v, v + (size_t)h0 * n, hl, c->n_old2new, h0)) return 1;
+                NC(g_nccl.AllReduce(c->v, c->v, (size_t)c->N * np, ncclUint32, ncclSum, c->comm, c->stream));
                 if (p) {
-                        CU(cudaMalloc(&pfull, sizeof(u32) * (size_t)gather_cap(c->n_off) * np));
-                        cudaError_t e = cudaMemcpyAsync(pfull + (size_t)n0 * np, c->p, sizeof(u32) * (size_t)ln * np, cudaMemcpyDeviceToDevice, c->stream);
-                        if (e != cudaSuccess || allgather_rows(c, pfull, c->n_off)) { cudaFree(pfull); return e != cudaSuccess ? fail(cudaGetErrorString(e)) : 1; }
+                        CU(cudaMalloc(&pfull, sizeof(u32) * full_rows * np));
+                        CU(cudaMemsetAsync(pfull, 0, sizeof(u32) * full_rows * np, c->stream));
+                        if (upload_rows(c, pfull, p + (size_t)h0 * n, hl, c->n_old2new, h0)) return 1;
+                        NC(g_nccl.AllReduce(pfull, pfull, (size_t)c->N * np, ncclUint32, ncclSum, c->comm, c->stream));
+                        CU(cudaMemcpyAsync(c->p, pfull + (size_t)n0 * np, sizeof(u32) * (size_t)ln * np, cudaMemcpyDeviceToDevice, c->stream));
                 }
-                int rc = mg_prepare(c, pfull);
-                cudaFree(pfull);
-                if (rc) return 1;
+        } else {
+                if (upload_rows(c, c->n_old2new ? c->v : c->v + (size_t)n0 * np, v + (size_t)n0 * n, ln, c->n_old2new, n0)) return 1;
+                if (c->world > 1 && allgather_rows(c, c->v, c->n_off)) return 1;
+                if (p && upload_rows(c, c->p, p + (size_t)n0 * n, ln, c->n_old2new, n0)) return 1;
+                if (p && c->mg_recur) {
+                        CU(cudaMalloc(&pfull, sizeof(u32) * full_rows * np));
+                        CU(cudaMemcpyAsync(pfull + (size_t)n0 * np, c->p, sizeof(u32) * (size_t)ln * np, cudaMemcpyDeviceToDevice, c->stream));
+                        if (allgather_rows(c, pfull, c->n_off)) return 1;
+                }
         }
+        if (!p) CU(cudaMemsetAsync(c->p, 0, sizeof(u32) * (size_t)(ln > 0 ? ln : 1) * np, c->stream));
+        CU(cudaMemsetAsync(c->tmp, 0, sizeof(u32) * (size_t)c->Mc * np, c->stream));
+        if (c->Av_full) CU(cudaMemsetAsync(c->Av_full, 0, sizeof(u32) * full_rows * np, c->stream));
+        else CU(cudaMemsetAsync(c->Av, 0, sizeof(u32) * (size_t)(ln > 0 ? ln : 1) * np, c->stream));
+        // invariant of the multi-GPU loop: tmp = S1 v (gathered), Tp = S1 p (local rows)
+        if (c->mg_recur && mg_prepare(c, p ? pfull : nullptr)) return 1;
         if (c->grid_on && grid_import(c, p)) return 1;
         c->ran_since_set = false;
         c->iters = n_iterations; c->stopped = 0;
@@ -2047,6 +2088,29 @@ static int download_state(blk_ctx *c, u32 *v, u32 *Av, u32 *p, u32 *ht, bool who
         if (c->grid_on && grid_export(c)) return 1;
         const bool all = whole && c->world > 1;
         const int64_t n0 = c->n0(), ln = c->n1() - c->n0(), m0 = c->m0(), lm = c->m1() - c->m0();
+        if (c->relabel_mg()) {
+                // device labels are scattered over the host order: gather the block over NVLink (device labels), then
+                // every rank unpermutes and downloads its share of HOST rows (all of them if it must return whole blocks)
+                const int64_t r0 = all ? 0 : c->h0(), cnt = all ? c->N : c->h1() - c->h0();
+                for (int which = 0; which < 3; which++) {
+                        u32 *dst = which == 0 ? v : (which == 1 ? Av : p);
+                        if (!dst) continue;
+                        u32 *full = c->v;
+                        if (which) {
+                                CU(cudaMalloc(&full, sizeof(u32) * (size_t)gather_cap(c->n_off) * np));
+                                if (cudaMemcpyAsync(full + (size_t)n0 * np, which == 1 ? c->Av : c->p, sizeof(u32) * (size_t)ln * np,
+                                                    cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) {
+                                        cudaFree(full);
+                                        return fail("blk_get_state: device copy failed");
+                                }
+                        }
+                        int rc = allgather_rows(c, full, c->n_off);
+                        if (!rc) rc = download_rows(c, dst + (size_t)r0 * n, full, cnt, c->n_old2new, r0);
+                        if (which) cudaFree(full);
+                        if (rc) return 1;
+                }
+                v = Av = p = nullptr;                  // done
+        }
         if (v) {
                 if (all) {
                         if (allgather_rows(c, c->v, c->n_off)) return 1;
@@ -2463,7 +2527,8 @@ int blk_get_info(blk_ctx *c, blk_info *info)
         }
         memset(info, 0, sizeof(*info));
         info->N = c->N; info->Mc = c->Mc;
-        info->local_N0 = c->n0(); info->local_N1 = c->n1();
+        // (with relabelled rows on several GPUs: the HOST rows this rank moves in blk_set_state / blk_get_state_local)
+        info->local_N0 = c->h0(); info->local_N1 = c->h1();
         info->local_M0 = c->m0(); info->local_M1 = c->m1();
         const SpOp *ops[2] = {&c->S1, &c->S2};
         for (int i = 0; i < 2; i++) {

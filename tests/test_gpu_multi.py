@@ -23,6 +23,9 @@ MODES = {                      # environment of the exchange modes (DESIGN.md se
     "norecur": {"BLK_RECUR": "0"},                          # plain all-gathers of v and tmp
     "pieces1": {"BLK_PIECES": "1"},
     "pieces8": {"BLK_PIECES": "8"},                         # shards disagree on the piece count for the small cases
+    # degree-sorted labels dealt to the ranks + hot prefix, forced on for test-sized matrices (default: blocks > 96 MB)
+    "hot": {"BLK_HOT_MIN_BYTES": "0", "BLK_HOT_BYTES": "8192"},
+    "hot_nccl": {"BLK_HOT_MIN_BYTES": "0", "BLK_HOT_BYTES": "8192", "BLK_EXCHANGE": "nccl"},
 }
 
 
@@ -46,7 +49,7 @@ def test_sharded_run_matches_oracle(lib, world):
     _torchrun(world, 29500 + world, {})
 
 
-@pytest.mark.parametrize("mode", [m for m in MODES if m != "push"])
+@pytest.mark.parametrize("mode", ["nccl", "push_kernel", "hot"])
 def test_exchange_modes_one_process_per_gpu(lib, mode):
     if _ngpus() < 2:
         pytest.skip("needs 2 GPUs")
@@ -60,9 +63,9 @@ def test_group_context_matches_oracle(lib, oracle, monkeypatch, world, mode):
     library, peer access between the devices of the process."""
     if _ngpus() < world:
         pytest.skip(f"needs {world} GPUs")
-    if world > 2 and mode not in ("push", "nccl", "pieces8"):
+    if world > 2 and mode not in ("push", "nccl", "pieces8", "hot"):
         pytest.skip("mode covered at world 2")
-    for k in ("BLK_EXCHANGE", "BLK_PUSH_AV", "BLK_RECUR", "BLK_PIECES"):
+    for k in ("BLK_EXCHANGE", "BLK_PUSH_AV", "BLK_RECUR", "BLK_PIECES", "BLK_HOT_MIN_BYTES", "BLK_HOT_BYTES"):
         monkeypatch.delenv(k, raising=False)
     for k, v in MODES[mode].items():
         monkeypatch.setenv(k, v)

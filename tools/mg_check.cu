@@ -94,9 +94,11 @@ static void run_rank(const Job &job, int rank, int world, int device, const void
         out->iters = it; out->stopped = st;
         if (profile) { int64_t l[BLK_PH_COUNT]; blk_get_phase_times(ctx, out->ph_ms, l); }
         if (want_state) {
+                // blk_get_state is collective (the blocks are gathered over NVLink): every rank asks, rank 0's copy is compared
                 const size_t pad = (size_t)blk_block_pad(job.rows, job.cols, job.n, 0);
                 out->v.assign(pad, 0); out->tmp.assign(pad, 0); out->Av.assign(pad, 0); out->p.assign(pad, 0);
                 if (blk_get_state(ctx, out->v.data(), out->tmp.data(), out->Av.data(), out->p.data())) { bail("blk_get_state"); return; }
+                if (rank != 0) { std::vector<uint32_t>().swap(out->v); std::vector<uint32_t>().swap(out->tmp); std::vector<uint32_t>().swap(out->Av); std::vector<uint32_t>().swap(out->p); }
         }
         blk_destroy(ctx);
 }
@@ -108,7 +110,7 @@ static bool run_world(const Job &job, int world, bool want_state, bool profile, 
         outs->assign((size_t)world, RankOut());
         std::vector<std::thread> th;
         for (int r = 0; r < world; r++)
-                th.emplace_back(run_rank, std::cref(job), r, world, r, (const void *)id, want_state && r == 0, profile && r == 0, &(*outs)[(size_t)r]);
+                th.emplace_back(run_rank, std::cref(job), r, world, r, (const void *)id, want_state, profile && r == 0, &(*outs)[(size_t)r]);
         for (auto &t : th) t.join();
         bool ok = true;
         for (int r = 0; r < world; r++)
@@ -118,6 +120,7 @@ static bool run_world(const Job &job, int world, bool want_state, bool profile, 
 
 int main(int argc, char **argv)
 {
+        setvbuf(stdout, nullptr, _IOLBF, 0);          // a run killed by `timeout` keeps what it printed
         if (argc < 3) { printf("usage: %s check|time W [rows cols nnz n prime iters]\n", argv[0]); return 2; }
         Job job;
         const bool check = !strcmp(argv[1], "check");
