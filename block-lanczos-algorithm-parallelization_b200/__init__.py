@@ -19,7 +19,7 @@ from .synth import SparseCOO                          # noqa: F401
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libblklanczos.so")
 
-BLK_ABI_VERSION = 1
+BLK_ABI_VERSION = 2
 BLK_MAX_N = 64
 BLK_NCCL_ID_BYTES = 128
 BLK_RANK_ALL = -1          # blk_params.rank: one context (one process) drives all `world` GPUs
@@ -55,6 +55,7 @@ class blk_info(C.Structure):
         ("local_M0", C.c_int64), ("local_M1", C.c_int64), ("nnz_local", C.c_int64 * 2),
         ("stored_local", C.c_int64 * 2), ("tiles", C.c_int64 * 2), ("n", C.c_int32), ("n_pad", C.c_int32),
         ("chunk_len", C.c_int32 * 2), ("groups_per_warp", C.c_int32), ("device_bytes", C.c_int64),
+        ("loop_mode", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

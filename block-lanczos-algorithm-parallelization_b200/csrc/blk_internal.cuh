@@ -43,6 +43,7 @@ struct SpOp {
         // row ENDS adds up the partial left in y by the tile where it started and the whead of the tiles in between.
         u32 *back = nullptr;       // [ntiles]    > 0: the row open at the start of this tile ends in it and started `back` tiles earlier
         u32 *ready = nullptr;      // [ntiles]    flag: the tile's part of the row open at its end is in memory (reset by the finisher)
+        bool crossing = false;     // some row crosses a tile border (k_spmv_fix / look-back has work to do)
         bool lookback = false;     // true (BLK_SPMV_FIX=lookback): finish those rows inside k_spmv; default: k_spmv_fix (faster, measured)
         size_t bytes = 0;
         // Row pieces for pipelining a product with the exchange of its result (multi-GPU): piece q is
@@ -224,6 +225,33 @@ int launch_dots_umma(int np, const ModP &m, int64_t rows, const u32 *v, const u3
                      const DevSmall *state, const SmallFuse &fuse, cudaStream_t st, int wide = -1);
 int launch_ortho_umma(int np, const ModP &m, int64_t rows, u32 *v, const u32 *Av, u32 *p, u32 *v_out, u32 *p_out,
                       const u32 *mats, const DevSmall *state, int force, cudaStream_t st, int variant = -1);
+// loop_coop.cu: the whole loop as one persistent cooperative kernel (single GPU, L2-resident problems, n_pad <= 16)
+struct LoopOp {
+        const uint2 *ent = nullptr;
+        const u32 *chunk_row = nullptr;
+        u32 *whead = nullptr;
+        const u32 *tail_row = nullptr, *span = nullptr;
+        int64_t ntiles = 0;
+        int Q = 0;
+        u32 rows = 0;
+        int crossing = 0;          // some row crosses a tile border: the fix-up phase (and its barrier) is needed
+};
+struct LoopArgs {
+        LoopOp s1, s2;             // tmp <- S1 v ; Av <- S2 tmp
+        u32 *v = nullptr, *tmp = nullptr, *Av = nullptr, *p = nullptr;
+        int64_t N = 0;
+        unsigned long long *sums = nullptr;
+        u32 *mats = nullptr;
+        DevSmall *state = nullptr;
+        ModP m;
+        int n = 0, max_iters = 0;
+        unsigned *bar = nullptr;   // two words: arrivals, release word of the serial barrier
+        unsigned long long *prof = nullptr;      // nullable: six phase clocks of block 0 (SM cycles, accumulated)
+};
+bool loop_coop_supported(int np);
+// thread blocks of the persistent kernel (0 + *why when it cannot run on the current device)
+int loop_coop_grid(int n, int np, const ModP &m, std::string *why);
+int launch_loop_coop(const LoopArgs &args, int n, int np, int grid, cudaStream_t st, std::string *err);
 // per-device one-time kernel attributes (call with the device current, outside stream capture)
 void dense_prepare(const Geometry &geo, const ModP &m);
 // n <-> n_pad repacking of row-major blocks (rows x n  <->  rows x np), `rows` rows starting at host row r0.

@@ -141,7 +141,10 @@ struct blk_ctx {
         enum { XCH_NCCL = 0, XCH_CE = 1, XCH_PUSH = 2 };
         int xch = XCH_NCCL;
         bool push_av_in_spmv = true;             // XCH_PUSH: Av from inside k_spmv (else k_push_rows per piece)
+        bool push_bulk = false;                  // XCH_PUSH: pieces travel by k_push_bulk (bulk-copy engine) instead of k_push_rows
         int push_ctas = 32;
+        int bulk_stages = 4;                     // k_push_bulk: ring of bulk_stages x bulk_chunk bytes of shared memory per CTA
+        unsigned bulk_chunk = 32768;
         std::vector<u32 *> peer_tmp, peer_av;    // [world] peer mappings of every rank's tmp / Av_full (own = local)
         std::vector<char> peer_ipc;              // [world] mapping came from cudaIpcOpenMemHandle (must be closed)
         std::vector<cudaStream_t> copy_streams;  // one per peer offset so that the copies use several copy engines
@@ -195,6 +198,13 @@ struct blk_ctx {
         int iters = 0, stopped = 0;
         bool tmp_is_spmv = false;               // tmp rows [0,Mc) hold S1*v of the current v (stop case)
         bool any_ortho = false;
+        // Persistent cooperative loop kernel (loop_coop.cu): single GPU, n_pad <= 16, operators + blocks L2-sized.
+        // One launch runs up to COOP_BATCH iterations; replaces the CUDA graph of six kernel nodes per iteration.
+        bool coop = false;
+        int coop_grid = 0;
+        unsigned *loop_bar = nullptr;            // 2 barrier words, then (8 bytes further) 6 u64 phase clocks
+        bool coop_prof = false;                  // BLK_LOOP_PROF=1: profiling mode keeps the persistent kernel and reads its phase clocks
+        static constexpr int COOP_BATCH = 1024;
         // graphs
         int use_graph = -1;
         cudaGraphExec_t graph = nullptr;
@@ -642,6 +652,67 @@ k_push_rows(const uint4 *__restrict__ src, PushTargets push, size_t first16, siz
         }
 }
 
+// The same exchange with the bulk-copy (TMA) engine instead of load/store instructions: ONE thread per CTA streams
+// 32 KB chunks of the piece through a ring in shared memory -- cp.async.bulk global -> shared (mbarrier completion),
+// then one cp.async.bulk shared -> peer memory per peer (a bulk group per chunk).  No registers, no LSU slots and no
+// warps to speak of: a CTA is 32 threads and 128 KB of shared memory, so it shares an SM with the resident blocks of
+// the sparse product (which use no shared memory) instead of displacing one of them.
+constexpr int PB_MAX_STAGES = 8;
+#ifndef BLK_BULK_TIMEOUT_CYCLES
+#define BLK_BULK_TIMEOUT_CYCLES 20000000000ll          // ~10 s of SM clock: trap instead of hanging the GPU
+#endif
+
+__global__ void __launch_bounds__(32)
+k_push_bulk(const unsigned char *__restrict__ src, PushTargets push, size_t first, size_t bytes, const DevSmall *__restrict__ state,
+            const int PB_STAGES, const unsigned PB_BYTES)
+{
+        extern __shared__ __align__(128) unsigned char pb_ring[];
+        __shared__ __align__(8) unsigned long long pb_full[PB_MAX_STAGES];
+        if (state && !state->do_ortho) return;            // the piece was not rewritten (halted iteration)
+        if (threadIdx.x != 0) return;
+        const size_t nchunks = (bytes + PB_BYTES - 1) / PB_BYTES;
+        const size_t mine = nchunks > blockIdx.x ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;      // chunks blockIdx.x + k * gridDim.x
+        if (mine == 0) return;
+        const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(pb_ring), bar0 = (uint32_t)__cvta_generic_to_shared(pb_full);
+        for (int s = 0; s < PB_STAGES; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8 * s), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        auto load = [&](size_t k) {
+                const size_t off = ((size_t)blockIdx.x + k * gridDim.x) * PB_BYTES;
+                const uint32_t len = (uint32_t)(bytes - off < PB_BYTES ? bytes - off : PB_BYTES);
+                const uint32_t bar = bar0 + 8 * (uint32_t)(k % PB_STAGES), dst = ring0 + PB_BYTES * (uint32_t)(k % PB_STAGES);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(len) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst), "l"(src + first + off), "r"(len), "r"(bar) : "memory");
+        };
+        for (size_t k = 0; k < mine && k < PB_STAGES - 1; k++) load(k);
+        for (size_t k = 0; k < mine; k++) {
+                const size_t off = ((size_t)blockIdx.x + k * gridDim.x) * PB_BYTES;
+                const uint32_t len = (uint32_t)(bytes - off < PB_BYTES ? bytes - off : PB_BYTES);
+                const uint32_t bar = bar0 + 8 * (uint32_t)(k % PB_STAGES), stage = ring0 + PB_BYTES * (uint32_t)(k % PB_STAGES);
+                const uint32_t parity = (uint32_t)(k / PB_STAGES) & 1u;
+                const long long t0 = clock64();
+                for (;;) {
+                        uint32_t ok;
+                        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+                        if (ok) break;
+                        if (clock64() - t0 > BLK_BULK_TIMEOUT_CYCLES) __trap();
+                }
+                for (int q = 0; q < push.n; q++)
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                     ::"l"(reinterpret_cast<unsigned char *>(push.y[q]) + first + off), "r"(stage), "r"(len) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                if (k + PB_STAGES - 1 < mine) {
+                        // the stage chunk k + STAGES - 1 will land in was last read by the stores of chunk k - 1
+                        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        load(k + PB_STAGES - 1);
+                }
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __threadfence_system();
+}
+
 // peers' copies of a block, addressed from row `row0` on (see PushTargets)
 PushTargets push_targets(const blk_ctx *c, const std::vector<u32 *> &peers, int64_t row0)
 {
@@ -669,6 +740,13 @@ int exchange_piece(blk_ctx *c, u32 *buf, const std::vector<u32 *> &peers, const 
         if (bytes == 0) return 0;
         if ((first | bytes) & 15) return fail("push exchange: piece not 16-byte aligned");
         PushTargets t = push_targets(c, peers, 0);
+        if (c->push_bulk) {
+                unsigned blocks = (unsigned)std::min<size_t>((size_t)c->push_ctas, (bytes + c->bulk_chunk - 1) / c->bulk_chunk);
+                k_push_bulk<<<blocks, 32, (size_t)c->bulk_stages * c->bulk_chunk, c->comm_stream>>>(reinterpret_cast<const unsigned char *>(buf), t, first, bytes,
+                                                                                                state, c->bulk_stages, c->bulk_chunk);
+                c->launches++;
+                return 0;
+        }
         const size_t count16 = bytes / 16;
         unsigned blocks = (unsigned)std::min<size_t>((size_t)c->push_ctas, (count16 + 511) / 512);
         k_push_rows<<<blocks, 512, 0, c->comm_stream>>>(reinterpret_cast<const uint4 *>(buf), t, first / 16, count16, state);
@@ -951,6 +1029,42 @@ int enqueue_iteration(blk_ctx *c, EventTimer *tm)
         if (tm) tm->end(c, k);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(e));
+        return 0;
+}
+
+// up to `iters` iterations in one launch of the persistent cooperative kernel (it stops by itself on `halt`)
+int enqueue_loop_coop(blk_ctx *c, int iters)
+{
+        auto op = [](const SpOp &s) {
+                LoopOp o;
+                o.ent = s.ent; o.chunk_row = s.chunk_row; o.whead = s.whead; o.tail_row = s.tail_row; o.span = s.span;
+                o.ntiles = s.ntiles; o.Q = s.Q; o.rows = (u32)s.rows; o.crossing = s.crossing ? 1 : 0;
+                return o;
+        };
+        LoopArgs a;
+        a.s1 = op(c->S1); a.s2 = op(c->S2);
+        a.v = c->v; a.tmp = c->tmp; a.Av = c->Av; a.p = c->p;
+        a.N = c->N;
+        a.sums = (unsigned long long *)c->sums; a.mats = c->mats; a.state = c->state; a.m = c->m;
+        a.n = c->geo.n; a.max_iters = iters; a.bar = c->loop_bar;
+        unsigned long long *clocks = reinterpret_cast<unsigned long long *>(c->loop_bar + 2);
+        const bool prof = c->profiling && c->coop_prof;
+        if (prof) { a.prof = clocks; CU(cudaMemsetAsync(clocks, 0, 6 * sizeof(unsigned long long), c->stream)); }
+        std::string err;
+        if (launch_loop_coop(a, c->geo.n, c->geo.np, c->coop_grid, c->stream, &err)) return fail(err);
+        c->launches += 1;
+        if (prof) {
+                // SM cycles of block 0 -> ms at the SM clock the driver reports (phases include the barrier that ends them)
+                unsigned long long h[6];
+                int khz = 0;
+                CU(cudaMemcpyAsync(h, clocks, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+                CU(cudaStreamSynchronize(c->stream));
+                CU(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device));
+                const double ms = khz > 0 ? 1.0 / khz : 0.0;
+                c->ph_ms[BLK_PH_SPMV1] += (double)(h[0] + h[1]) * ms; c->ph_ms[BLK_PH_SPMV2] += (double)(h[2] + h[3]) * ms;
+                c->ph_ms[BLK_PH_DOTS] += (double)h[4] * ms; c->ph_ms[BLK_PH_ORTHO] += (double)h[5] * ms;
+                c->ph_ms[BLK_PH_EXCHANGE] += (double)(h[1] + h[3]) * ms;     // (reported apart: the two fix-up phases)
+        }
         return 0;
 }
 
@@ -1503,6 +1617,17 @@ int create_multi(blk_ctx *c, const blk_params *prm, bool grid_req)
         }
         c->xch = want;
         if (const char *ea = getenv("BLK_PUSH_AV")) c->push_av_in_spmv = strcmp(ea, "kernel") != 0;     // kernel | spmv
+        if (const char *eb = getenv("BLK_PUSH_COPY")) {
+                if (!strcmp(eb, "bulk")) c->push_bulk = true;
+                else if (strcmp(eb, "rows")) return fail("BLK_PUSH_COPY must be rows or bulk");
+        }
+        if (c->push_bulk) {
+                c->push_ctas = 16;
+                if (const char *es = getenv("BLK_BULK_STAGES")) c->bulk_stages = std::max(2, std::min(PB_MAX_STAGES, atoi(es)));
+                if (const char *ek = getenv("BLK_BULK_CHUNK")) c->bulk_chunk = (unsigned)std::max(1024, std::min(65536, atoi(ek))) & ~127u;
+                if ((size_t)c->bulk_stages * c->bulk_chunk > 200 * 1024) return fail("BLK_BULK_STAGES x BLK_BULK_CHUNK exceeds the shared memory of an SM");
+                CU(cudaFuncSetAttribute(k_push_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, c->bulk_stages * (int)c->bulk_chunk));
+        }
         if (const char *ec = getenv("BLK_PUSH_CTAS")) c->push_ctas = std::max(1, std::min(1024, atoi(ec)));
         if (c->xch != blk_ctx::XCH_NCCL) {
                 CU(cudaMalloc(&c->barrier_word, sizeof(u64)));
@@ -1709,6 +1834,28 @@ int create_impl(blk_ctx *c, const blk_params *prm)
         {
                 const char *e = getenv("BLK_FUSE_SMALL");
                 c->fuse_small = world == 1 && np <= 32 && !(e && e[0] == '0');
+        }
+        {
+                // BLK_LOOP=graph | coop | auto (default): the persistent loop kernel serves problems that live in L2, where an
+                // iteration is latency-bound; bandwidth-bound problems keep the chain of kernels (tensor-core dense phases,
+                // hot-prefix gathers), which the persistent kernel does not have.
+                const char *e = getenv("BLK_LOOP");
+                const bool force = e && !strcmp(e, "coop"), off = e && !strcmp(e, "graph");
+                if (e && !force && !off && strcmp(e, "auto")) return fail("BLK_LOOP must be graph, coop or auto");
+                const size_t working_set = c->S1.bytes + c->S2.bytes + c->block_bytes - 2 * blk_ctx::STAGE_BYTES;
+                const bool eligible = world == 1 && !c->colblocks && loop_coop_supported(np) && !c->S1.lookback && !c->S2.lookback &&
+                                      !c->S1.hot_cols && c->N > 0 && c->Mc > 0;
+                if (force && !eligible) return fail("BLK_LOOP=coop: the persistent loop kernel needs one GPU, n <= 16 and the default product kernels");
+                if (eligible && !off && (force || working_set <= (size_t)48 << 20)) {
+                        std::string why;
+                        c->coop_grid = loop_coop_grid(c->geo.n, np, c->m, &why);
+                        if (c->coop_grid > 0) {
+                                CU(cudaMalloc(&c->loop_bar, 2 * sizeof(unsigned) + 6 * sizeof(unsigned long long)));
+                                CU(cudaMemsetAsync(c->loop_bar, 0, 2 * sizeof(unsigned) + 6 * sizeof(unsigned long long), c->stream));
+                                c->coop = true;
+                                c->coop_prof = env_flag("BLK_LOOP_PROF");
+                        } else if (force) return fail("BLK_LOOP=coop: " + why);
+                }
         }
         c->check = env_flag("BLK_CHECK");
         if (const char *ef = getenv("BLK_CHECK_FAULT")) c->check_fault = atoi(ef);
@@ -1937,7 +2084,7 @@ int blk_destroy(blk_ctx *c)
         cudaFree(c->Tp); cudaFree(c->U); cudaFree(c->tmp_prev);
         cudaFree(c->mats); cudaFree(c->sums); cudaFree(c->state); cudaFree(c->dots_counter);
         cudaFree(c->n_old2new); cudaFree(c->n_new2old);
-        cudaFree(c->stage);
+        cudaFree(c->stage); cudaFree(c->loop_bar);
         if (c->h_state) cudaFreeHost(c->h_state);
         for (auto e : c->ev_copies) cudaEventDestroy(e);
         for (auto st : c->copy_streams) cudaStreamDestroy(st);
@@ -2028,6 +2175,9 @@ int blk_iterate(blk_ctx *c, int32_t max_iters, int32_t *iters_total, int32_t *st
                 if (push_state(c)) return 1;
                 bool graph = c->use_graph == 1 || (c->use_graph < 0 && c->world == 1 && max_iters >= 4);
                 if (c->profiling || c->world > 1 || c->colblocks) graph = false;
+                // (use_graph == 0 asks for the plain chain of kernels; per-phase profiling needs kernel boundaries)
+                const bool coop = c->coop && c->use_graph != 0 && (!c->profiling || c->coop_prof);
+                if (coop) graph = false;
                 EventTimer tm;
                 int done = 0;
                 if (graph && !c->graph) {
@@ -2036,10 +2186,12 @@ int blk_iterate(blk_ctx *c, int32_t max_iters, int32_t *iters_total, int32_t *st
                         done = 1;
                         if (build_graph(c)) return 1;
                 }
-                const int check_every = graph ? 16 * blk_ctx::GRAPH_ITERS : 64;
+                const int check_every = coop ? blk_ctx::COOP_BATCH : (graph ? 16 * blk_ctx::GRAPH_ITERS : 64);
                 while (done < max_iters) {
                         int batch = std::min(check_every, max_iters - done);
-                        if (graph) {
+                        if (coop) {
+                                if (enqueue_loop_coop(c, batch)) return 1;
+                        } else if (graph) {
                                 int ng = (batch + blk_ctx::GRAPH_ITERS - 1) / blk_ctx::GRAPH_ITERS;
                                 for (int i = 0; i < ng; i++) CU(cudaGraphLaunch(c->graph, c->stream));
                                 c->launches += (int64_t)ng * blk_ctx::GRAPH_ITERS * kernels_per_iteration(c);
@@ -2539,6 +2691,7 @@ int blk_get_info(blk_ctx *c, blk_info *info)
         }
         info->n = c->geo.n; info->n_pad = c->geo.np; info->groups_per_warp = c->geo.G;
         info->device_bytes = (int64_t)(c->S1.bytes + c->S2.bytes + c->block_bytes);
+        info->loop_mode = (c->coop && c->use_graph != 0) ? 1 : 0;
         return 0;
 }
 

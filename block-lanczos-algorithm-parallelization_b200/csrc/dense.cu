@@ -11,31 +11,11 @@
 // n_pad (power of two >= n, extra columns are zero and stay zero through every phase).
 #include "blk_internal.cuh"
 #include "small_body.cuh"
+#include "dense_body.cuh"
 
 namespace {
 
 constexpr int DOTS_TB = 256;
-
-template <int V> struct VecD;
-template <> struct VecD<1> { typedef unsigned int T; };
-template <> struct VecD<2> { typedef uint2 T; };
-template <> struct VecD<4> { typedef uint4 T; };
-
-template <int V> __device__ __forceinline__ void ldv(u32 (&o)[V], const u32 *p)
-{
-        typename VecD<V>::T t = *reinterpret_cast<const typename VecD<V>::T *>(p);
-        const u32 *w = reinterpret_cast<const u32 *>(&t);
-#pragma unroll
-        for (int k = 0; k < V; k++) o[k] = w[k];
-}
-template <int V> __device__ __forceinline__ void stv(u32 *p, const u32 (&o)[V])
-{
-        typename VecD<V>::T t;
-        u32 *w = reinterpret_cast<u32 *>(&t);
-#pragma unroll
-        for (int k = 0; k < V; k++) w[k] = o[k];
-        *reinterpret_cast<typename VecD<V>::T *>(p) = t;
-}
 
 // ------------------------------------------------------------------------------------------
 // dots: a team of T = (NP/TI)^2 threads owns the NP x NP outputs (TI x TI register tile per
@@ -47,92 +27,13 @@ k_dots(int64_t rows, const u32 *__restrict__ v, const u32 *__restrict__ Av, unsi
        ModP m, const DevSmall *state, SmallFuse fuse)
 {
         pdl_prologue();
-        constexpr int TI = NP < 4 ? NP : 4;
-        constexpr int PER = NP / TI;          // tiles per dimension
-        constexpr int T = PER * PER;          // threads per team
-        constexpr int TEAMS = DOTS_TB / T;
-        constexpr int FE = FOLD ? FOLD : 64;  // rows between folds
         if (state && state->halt) {
                 // a halted iteration must not re-run orthogonalize (k_small would have cleared the flag)
                 if (fuse.counter && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) fuse.state->do_ortho = 0;
                 return;
         }
 
-        const int tid = threadIdx.x;
-        const int team = tid / T, tt = tid % T;
-        const int i0 = (tt / PER) * TI, j0 = (tt % PER) * TI;
-        u64 a1[TI][TI], a2[TI][TI];
-#pragma unroll
-        for (int a = 0; a < TI; a++)
-#pragma unroll
-                for (int b = 0; b < TI; b++) { a1[a][b] = 0; a2[a][b] = 0; }
-
-        const int64_t stride = (int64_t)gridDim.x * TEAMS;
-        int since = 0;
-        for (int64_t r = (int64_t)blockIdx.x * TEAMS + team; r < rows; r += stride) {
-                u32 vi[TI], ai[TI], aj[TI];
-                ldv<TI>(vi, v + r * NP + i0);
-                ldv<TI>(ai, Av + r * NP + i0);
-                ldv<TI>(aj, Av + r * NP + j0);
-#pragma unroll
-                for (int a = 0; a < TI; a++)
-#pragma unroll
-                        for (int b = 0; b < TI; b++) {
-                                mp_mac(a1[a][b], vi[a], aj[b]);
-                                mp_mac(a2[a][b], ai[a], aj[b]);
-                        }
-                if (++since == FE) {
-                        since = 0;
-#pragma unroll
-                        for (int a = 0; a < TI; a++)
-#pragma unroll
-                                for (int b = 0; b < TI; b++) { mp_fold(a1[a][b], m); mp_fold(a2[a][b], m); }
-                }
-        }
-
-        // block result -> global u64 sums (integer addition: order-free, hence deterministic).
-        // Every addend is a canonical residue < 2^31, so 2^33 blocks could not overflow.
-        // Teams inside a warp are combined with shuffles first (mod-p adds on u32).
-        constexpr int TPW = T < 32 ? 32 / T : 1;       // teams per warp
-        u32 r1[TI][TI], r2[TI][TI];
-#pragma unroll
-        for (int a = 0; a < TI; a++)
-#pragma unroll
-                for (int b = 0; b < TI; b++) {
-                        u32 x = mp_reduce(a1[a][b], m), y = mp_reduce(a2[a][b], m);
-#pragma unroll
-                        for (int off = T; off < T * TPW; off <<= 1) {
-                                x = mp_add(x, __shfl_xor_sync(0xffffffffu, x, off), m);
-                                y = mp_add(y, __shfl_xor_sync(0xffffffffu, y, off), m);
-                        }
-                        r1[a][b] = x; r2[a][b] = y;
-                }
-        const bool writer = T >= 32 || (tid & 31) < T;  // one team per warp carries the warp's result
-        if (TEAMS == 1) {
-#pragma unroll
-                for (int a = 0; a < TI; a++)
-#pragma unroll
-                        for (int b = 0; b < TI; b++) {
-                                atomicAdd(&sums[(i0 + a) * NP + j0 + b], (unsigned long long)r1[a][b]);
-                                atomicAdd(&sums[NP * NP + (i0 + a) * NP + j0 + b], (unsigned long long)r2[a][b]);
-                        }
-        } else {
-                __shared__ unsigned long long acc[TEAMS == 1 ? 1 : 2 * NP * NP];
-                for (int e = tid; e < 2 * NP * NP; e += DOTS_TB) acc[e] = 0;
-                __syncthreads();
-                if (writer) {
-#pragma unroll
-                        for (int a = 0; a < TI; a++)
-#pragma unroll
-                                for (int b = 0; b < TI; b++) {
-                                        atomicAdd(&acc[(i0 + a) * NP + j0 + b], (unsigned long long)r1[a][b]);
-                                        atomicAdd(&acc[NP * NP + (i0 + a) * NP + j0 + b], (unsigned long long)r2[a][b]);
-                                }
-                }
-                __syncthreads();
-                for (int e = tid; e < 2 * NP * NP; e += DOTS_TB)
-                        atomicAdd(&sums[e], (unsigned long long)mp_reduce(acc[e], m));
-        }
+        dots_block<NP, FOLD, 0, DOTS_TB>(rows, v, Av, sums, m, blockIdx.x, gridDim.x);
         if (fuse.counter && last_block_done(fuse.counter, gridDim.x)) {
                 extern __shared__ u32 sm_fused[];
                 small_body(fuse.n, NP, sums, fuse.mats, fuse.state, 0, m, sm_fused);
@@ -168,11 +69,6 @@ k_ortho(int64_t rows, const u32 *v, const u32 *__restrict__ Av, const u32 *p, u3
         const u32 *__restrict__ mats, ModP m, const DevSmall *__restrict__ state, int force)
 {
         pdl_prologue();
-        constexpr int TPR = NP / JT;
-        constexpr int KV = NP < 4 ? NP : 4;
-        constexpr int JV = JT < 4 ? JT : 4;
-        constexpr int FV = FOLD ? FOLD / 2 : 32;     // k-steps between folds of accV (2 products per k)
-        constexpr int FP = FOLD ? FOLD : 64;         // ... of accP (1 product per k)
         extern __shared__ u32 sm[];
         u32 *C = sm, *D = C + NP * NP, *Wm = D + NP * NP, *dm = Wm + NP * NP;
         if (!force && !state->do_ortho) return;
@@ -184,72 +80,7 @@ k_ortho(int64_t rows, const u32 *v, const u32 *__restrict__ Av, const u32 *p, u3
         for (int e = threadIdx.x; e < NP; e += ORTHO_TB) dm[e] = mats[MAT_D * NP * NP + e];
         __syncthreads();
 
-        const int64_t gid = (int64_t)blockIdx.x * ORTHO_TB + threadIdx.x;
-        const int64_t r = gid / TPR;
-        const int j0 = (int)(gid % TPR) * JT;
-        const bool active = r < rows;
-        u64 accV[JT], accP[JT];
-#pragma unroll
-        for (int j = 0; j < JT; j++) { accV[j] = 0; accP[j] = 0; }
-        u32 nv[JT], npw[JT];
-        if (active) {
-                const u32 *vr = v + r * NP, *pr = p + r * NP;
-#pragma unroll
-                for (int k0 = 0; k0 < NP; k0 += KV) {
-                        u32 vk[KV], pk[KV];
-                        ldv<KV>(vk, vr + k0);
-                        ldv<KV>(pk, pr + k0);
-#pragma unroll
-                        for (int kk = 0; kk < KV; kk++) {
-                                const int k = k0 + kk;
-#pragma unroll
-                                for (int jj = 0; jj < JT; jj += JV) {
-                                        u32 cc[JV], dd[JV], ww[JV];
-                                        ldv<JV>(cc, C + k * NP + j0 + jj);
-                                        ldv<JV>(dd, D + k * NP + j0 + jj);
-                                        ldv<JV>(ww, Wm + k * NP + j0 + jj);
-#pragma unroll
-                                        for (int j = 0; j < JV; j++) {
-                                                mp_mac(accV[jj + j], vk[kk], cc[j]);
-                                                mp_mac(accV[jj + j], pk[kk], dd[j]);
-                                                mp_mac(accP[jj + j], vk[kk], ww[j]);
-                                        }
-                                }
-                                if ((k + 1) % FV == 0) {
-#pragma unroll
-                                        for (int j = 0; j < JT; j++) mp_fold(accV[j], m);
-                                }
-                                if ((k + 1) % FP == 0) {
-#pragma unroll
-                                        for (int j = 0; j < JT; j++) mp_fold(accP[j], m);
-                                }
-                        }
-                }
-#pragma unroll
-                for (int jj = 0; jj < JT; jj += JV) {
-                        u32 av[JV], vb[JV], pb[JV];
-                        ldv<JV>(av, Av + r * NP + j0 + jj);
-                        ldv<JV>(vb, vr + j0 + jj);
-                        ldv<JV>(pb, pr + j0 + jj);
-#pragma unroll
-                        for (int j = 0; j < JV; j++) {
-                                bool dj = dm[j0 + jj + j] != 0;
-                                nv[jj + j] = mp_add(mp_reduce(accV[jj + j], m), dj ? av[j] : vb[j], m);
-                                npw[jj + j] = mp_add(mp_reduce(accP[jj + j], m), dj ? 0u : pb[j], m);
-                        }
-                }
-        }
-        if (TPR > 1) __syncwarp();      // in place: every lane of the row has read v, p before anyone writes
-        if (active) {
-#pragma unroll
-                for (int jj = 0; jj < JT; jj += JV) {
-                        u32 a[JV], b[JV];
-#pragma unroll
-                        for (int j = 0; j < JV; j++) { a[j] = nv[jj + j]; b[j] = npw[jj + j]; }
-                        stv<JV>(v_out + r * NP + j0 + jj, a);
-                        stv<JV>(p_out + r * NP + j0 + jj, b);
-                }
-        }
+        ortho_slot<NP, JT, FOLD, 0>((int64_t)blockIdx.x * ORTHO_TB + threadIdx.x, rows, v, Av, p, v_out, p_out, C, D, Wm, dm, m);
 }
 
 // host-layout rows (n per row) -> device rows (np per row, zero padded).  Row r of src goes to device row

@@ -115,7 +115,7 @@ __global__ void k_chunk_rows(int64_t nchunks, int Q, int64_t stored, int64_t row
 
 __global__ void k_tile_tails(int64_t ntiles, int64_t tile, int64_t stored, int64_t rows,
                              const u64 *__restrict__ rowptr, u32 *__restrict__ tail_row,
-                             u32 *__restrict__ span, u32 *__restrict__ back)
+                             u32 *__restrict__ span, u32 *__restrict__ back, int *__restrict__ any_crossing)
 {
         int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
         if (t >= ntiles) return;
@@ -131,7 +131,10 @@ __global__ void k_tile_tails(int64_t ntiles, int64_t tile, int64_t stored, int64
         }
         tail_row[t] = tr;
         span[t] = sp;
-        if (sp) back[t + sp] = sp;          // (a tile finishes at most one such row: the one open at its start)
+        if (sp) {
+                back[t + sp] = sp;          // (a tile finishes at most one such row: the one open at its start)
+                *any_crossing = 1;
+        }
 }
 
 }  // namespace
@@ -286,10 +289,14 @@ std::string build_operator(SpOp *op, const Geometry &geo, int chunk_len, int64_t
         CKC(cudaGetLastError());
         k_chunk_rows<<<nblk(nchunks), TB, 0, st>>>(nchunks, op->Q, op->stored, rows, rowptr, op->chunk_row);
         CKC(cudaGetLastError());
+        CKC(cudaMemsetAsync(bad, 0, sizeof(int), st));
         k_tile_tails<<<nblk(op->ntiles), TB, 0, st>>>(op->ntiles, tile, op->stored, rows, rowptr,
-                                                      op->tail_row, op->span, op->back);
+                                                      op->tail_row, op->span, op->back, bad);
         CKC(cudaGetLastError());
+        int h_cross = 0;
+        CKC(cudaMemcpyAsync(&h_cross, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
         CKC(cudaStreamSynchronize(st));
+        op->crossing = h_cross != 0;
 
         // ---- row pieces (see SpOp): boundaries at tile multiples; the row that straddles a boundary
         // is finished by the fix-up of the piece in which it ends

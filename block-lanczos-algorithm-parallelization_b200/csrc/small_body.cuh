@@ -81,11 +81,14 @@ static __device__ __noinline__ int gj_sweep(GjBuf *buf, int *cur, bool carry_w, 
 // mode 0: full step; 1: reduce dots only; 2: semi_inverse of mats[VTAV]; 3: coefficients only
 // Runs on ONE thread block of any size (all of its threads must call it); `sm` is a shared-memory
 // scratch of small_smem_words(n) u32.
-static __device__ __noinline__ void small_body(int n, int np, unsigned long long *sums, u32 *mats, DevSmall *state,
+static __device__ __noinline__ void small_body(int n, int np, unsigned long long *sums, u32 *mats, DevSmall *state_,
                                         int mode, const ModP &m, u32 *sm)
 {
         const int tid = threadIdx.x, SMALL_TB = blockDim.x;
         const int nn = n * n, npp = np * np;
+        // (in the persistent loop kernel successive iterations may run this stage on different thread blocks: the few
+        // flag words are read and written as volatile, i.e. at L2)
+        volatile DevSmall *state = state_;
         u32 *A = sm;               // vtAv   (n x n)
         u32 *B = A + nn;           // vtAAv
         GjBuf buf[2];
@@ -105,7 +108,7 @@ static __device__ __noinline__ void small_body(int n, int np, unsigned long long
                 for (int e = tid; e < 2 * npp; e += SMALL_TB) {
                         int which = e / npp, r = e - which * npp;
                         int i = r / np, j = r - i * np;
-                        u32 val = mp_reduce(sums[e], m);
+                        u32 val = mp_reduce(__ldcg(&sums[e]), m);        // (added by other blocks' atomics: read at L2)
                         sums[e] = 0;
                         if (i < n && j < n) (which ? B : A)[i * n + j] = val;
                         mats[(which ? MAT_VTAAV : MAT_VTAV) * npp + r] = val;

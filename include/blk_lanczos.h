@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define BLK_ABI_VERSION 1
+#define BLK_ABI_VERSION 2
 #define BLK_MAX_N 64
 #define BLK_NCCL_ID_BYTES 128
 /* blk_params.rank value: this process drives ALL `world` GPUs (devices device ... device+world-1) through one
@@ -192,6 +192,9 @@ typedef struct blk_info {
         int64_t tiles[2];              /* warp tiles */
         int32_t n, n_pad, chunk_len[2], groups_per_warp;
         int64_t device_bytes;          /* resident bytes (matrix layouts + blocks) */
+        int32_t loop_mode;             /* how blk_iterate runs the loop: 0 chain of kernels / CUDA graph, 1 one persistent
+                                          cooperative kernel (L2-resident problems on one GPU, BLK_LOOP) */
+        int32_t reserved;
 } blk_info;
 int  blk_get_info(blk_ctx *ctx, blk_info *info);
 

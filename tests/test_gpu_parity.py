@@ -141,17 +141,25 @@ def test_dense_functions_many_tiles(lib, oracle, n, p):
             assert np.array_equal(go[0], wo[0]) and np.array_equal(go[1], wo[1]), (N, "ortho")
 
 
+# the three ways blk_iterate can run the loop: (name, blk_params.use_graph, BLK_LOOP)
+LOOP_MODES = (("chain", 0, "graph"),      # one kernel launch per phase
+              ("graph", 1, "graph"),      # CUDA graph of 16 iterations
+              ("coop", -1, "auto"))       # one persistent cooperative kernel (default for L2-sized problems, n <= 16)
+
+
 @pytest.mark.parametrize("name", golden_cases("loop_"))
-def test_loop_state_matches_reference_golden(lib, name):
+def test_loop_state_matches_reference_golden(lib, name, monkeypatch):
     z, M = load_golden(name)
     p, n, right, K = int(z["p"]), int(z["n"]), bool(z["right"]), int(z["K"])
     N = M.ncols if right else M.nrows
-    for graph in (0, 1):
+    for mode, graph, env in LOOP_MODES:
+        monkeypatch.setenv("BLK_LOOP", env)
         with lib.BlockLanczos(M.reduced(p), n=n, prime=p, right=right, use_graph=graph) as ctx:
+            assert ctx.info()["loop_mode"] == (1 if mode == "coop" and n <= 16 else 0)
             st = ctx.block_lanczos(z["v0"][:N * n], stop_after=K, batch=3)
             assert st["iters"] == K and not st["stopped"]
             for k, g in (("v", "v"), ("tmp", "tmp"), ("Av", "Av"), ("p", "pblk")):
-                assert np.array_equal(st[k], z[g]), (k, graph)
+                assert np.array_equal(st[k], z[g]), (k, mode)
             sm = ctx.get_small()
             for k in ("vtAv", "vtAAv", "winv", "d"):
                 assert np.array_equal(sm[k], z[k]), k
@@ -356,12 +364,14 @@ def test_runtime_correctness_tests(lib, oracle, monkeypatch):
         Mp = M.reduced(p)
         N = M.ncols if right else M.nrows
         v0 = oracle.start_block(N * n, p)
-        for graph in (0, 1):
+        for mode, graph, env in LOOP_MODES:
+            monkeypatch.setenv("BLK_LOOP", env)
             with lib.BlockLanczos(Mp, n=n, prime=p, right=right, use_graph=graph) as ctx:
                 got = ctx.block_lanczos(v0, stop_after=12, batch=5)
             want = oracle.lanczos_run(Mp, n, p, right, stop_after=12)
             for k in ("v", "tmp", "Av", "p"):
-                assert np.array_equal(got[k], want[k]), (n, graph, k)
+                assert np.array_equal(got[k], want[k]), (n, mode, k)
+        monkeypatch.delenv("BLK_LOOP")
         monkeypatch.setenv("BLK_CHECK_FAULT", "6")
         with lib.BlockLanczos(Mp, n=n, prime=p, right=right) as ctx:
             ctx.set_state(v0)
@@ -372,3 +382,45 @@ def test_runtime_correctness_tests(lib, oracle, monkeypatch):
             want = oracle.lanczos_run(Mp, n, p, right, stop_after=5)
             assert np.array_equal(st["v"], want["v"]) and np.array_equal(st["p"], want["p"])
         monkeypatch.delenv("BLK_CHECK_FAULT")
+
+
+@pytest.mark.parametrize("n,p", [(1, P_FERMAT), (2, P_CAP), (3, P_MERSENNE), (4, P_FERMAT), (5, 7), (8, P_MERSENNE), (13, 1048583),
+                                 (16, P_MERSENNE), (16, P_CAP)])
+def test_persistent_loop_kernel_matches_oracle(lib, oracle, monkeypatch, n, p):
+    """loop_coop.cu: the loop as one cooperative kernel (grid barriers between the phases).  Runs to termination and
+    runs cut by --stop-after, in batches that end inside and outside a launch, rows crossing tile borders (giant
+    rows) and operators without any, empty rows, Mc > N -- every block identical to the oracle's."""
+    monkeypatch.setenv("BLK_LOOP", "coop")
+    s = lib.synth
+    cases = [(s.powerlaw_rows(3000, 2700, mean=9, seed=3, with_empty_rows=11), False, 9, 4),
+             (s.uniform_nnz(2500, 3100, 30000, seed=4, order="col"), True, 7, 7),
+             (s.powerlaw_rows(700, 650, mean=6, seed=5), False, -1, 64),             # run to the end
+             (s.powerlaw_rows(1200, 1500, mean=7, seed=6), False, 6, 1),              # Mc > N, one iteration per launch
+             (s.uniform_rows(300, 280, 8, seed=8), False, -1, 1000)]                  # 8 entries in every row: no row crosses a tile
+    for ci, (M, right, stop_after, batch) in enumerate(cases):
+        Mp = M.reduced(p)
+        N = M.ncols if right else M.nrows
+        v0 = oracle.start_block(N * n, p)
+        with lib.BlockLanczos(Mp, n=n, prime=p, right=right) as ctx:
+            assert ctx.info()["loop_mode"] == 1
+            got = ctx.block_lanczos(v0, stop_after=stop_after, batch=batch)
+            want = oracle.lanczos_run(Mp, n, p, right, stop_after=stop_after)
+            assert got["iters"] == want["iters"] and got["stopped"] == want["stopped"], (ci, got["iters"], want["iters"])
+            for k in ("v", "tmp", "Av", "p"):
+                assert np.array_equal(got[k], want[k]), (ci, n, p, k)
+            assert ctx.final_check() == (bool(want["v"].any()),
+                                         not oracle.sparse_matrix_vector_product(Mp, want["v"], not right, n, p).any())
+
+
+def test_persistent_loop_kernel_is_the_default_for_small_problems(lib, monkeypatch):
+    monkeypatch.delenv("BLK_LOOP", raising=False)
+    M = lib.synth.uniform_rows(2000, 1900, 20, seed=2)
+    with lib.BlockLanczos(M.reduced(P_FERMAT), n=4, prime=P_FERMAT) as ctx:
+        assert ctx.info()["loop_mode"] == 1
+    with lib.BlockLanczos(M.reduced(P_FERMAT), n=4, prime=P_FERMAT, use_graph=0) as ctx:
+        assert ctx.info()["loop_mode"] == 0
+    with lib.BlockLanczos(M.reduced(P_FERMAT), n=32, prime=P_FERMAT) as ctx:            # n_pad > 16: CUDA graph
+        assert ctx.info()["loop_mode"] == 0
+    monkeypatch.setenv("BLK_LOOP", "coop")
+    with pytest.raises(lib.BlkError, match="BLK_LOOP=coop"):
+        lib.BlockLanczos(M.reduced(P_FERMAT), n=32, prime=P_FERMAT)

@@ -26,5 +26,5 @@ except Exception as e:
     print("bench FAILED", e, open("gpurun_out/r2_i_bench${G}.err").read()[-1500:])
 PY
 timeout 300 python -m pytest tests/test_gpu_multi.py -q --timeout=250 -x \
-  -k "(group_context and ${G}-hot) or (block_grid and 4x2) or (sharded and ${G})" > gpurun_out/r2_i_pytest${G}.log 2>&1
+  -k "(group_context and hot-${G}) or (block_grid and 4x2) or (sharded and ${G}])" > gpurun_out/r2_i_pytest${G}.log 2>&1
 tail -4 gpurun_out/r2_i_pytest${G}.log
