@@ -1836,9 +1836,11 @@ int create_impl(blk_ctx *c, const blk_params *prm)
                 c->fuse_small = world == 1 && np <= 32 && !(e && e[0] == '0');
         }
         {
-                // BLK_LOOP=graph | coop | auto (default): the persistent loop kernel serves problems that live in L2, where an
-                // iteration is latency-bound; bandwidth-bound problems keep the chain of kernels (tensor-core dense phases,
-                // hot-prefix gathers), which the persistent kernel does not have.
+                // BLK_LOOP=coop runs the loop as ONE persistent cooperative kernel (loop_coop.cu) instead of a CUDA graph of six
+                // kernel nodes per iteration.  Measured on BASELINE configs 1-3 (profiles/r02_loop_coop.txt): 29.9 / 44.3 / 103.8 us
+                // per iteration against 26.1 / 41.2 / 75.3 for the graph -- a grid barrier costs what a graph edge costs
+                // (~1.5-2 us), and one block of 16 warps per SM hides the latency of the products worse than three blocks
+                // of 8 -- so the graph stays the default (BLK_LOOP=graph | auto) and the persistent kernel is an opt-in.
                 const char *e = getenv("BLK_LOOP");
                 const bool force = e && !strcmp(e, "coop"), off = e && !strcmp(e, "graph");
                 if (e && !force && !off && strcmp(e, "auto")) return fail("BLK_LOOP must be graph, coop or auto");
@@ -1846,7 +1848,8 @@ int create_impl(blk_ctx *c, const blk_params *prm)
                 const bool eligible = world == 1 && !c->colblocks && loop_coop_supported(np) && !c->S1.lookback && !c->S2.lookback &&
                                       !c->S1.hot_cols && c->N > 0 && c->Mc > 0;
                 if (force && !eligible) return fail("BLK_LOOP=coop: the persistent loop kernel needs one GPU, n <= 16 and the default product kernels");
-                if (eligible && !off && (force || working_set <= (size_t)48 << 20)) {
+                (void)working_set;
+                if (eligible && force) {
                         std::string why;
                         c->coop_grid = loop_coop_grid(c->geo.n, np, c->m, &why);
                         if (c->coop_grid > 0) {

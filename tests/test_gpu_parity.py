@@ -144,7 +144,7 @@ def test_dense_functions_many_tiles(lib, oracle, n, p):
 # the three ways blk_iterate can run the loop: (name, blk_params.use_graph, BLK_LOOP)
 LOOP_MODES = (("chain", 0, "graph"),      # one kernel launch per phase
               ("graph", 1, "graph"),      # CUDA graph of 16 iterations
-              ("coop", -1, "auto"))       # one persistent cooperative kernel (default for L2-sized problems, n <= 16)
+              ("coop", -1, "coop"))       # one persistent cooperative kernel (opt-in; n_pad <= 16)
 
 
 @pytest.mark.parametrize("name", golden_cases("loop_"))
@@ -153,9 +153,11 @@ def test_loop_state_matches_reference_golden(lib, name, monkeypatch):
     p, n, right, K = int(z["p"]), int(z["n"]), bool(z["right"]), int(z["K"])
     N = M.ncols if right else M.nrows
     for mode, graph, env in LOOP_MODES:
+        if mode == "coop" and n > 16:
+            continue
         monkeypatch.setenv("BLK_LOOP", env)
         with lib.BlockLanczos(M.reduced(p), n=n, prime=p, right=right, use_graph=graph) as ctx:
-            assert ctx.info()["loop_mode"] == (1 if mode == "coop" and n <= 16 else 0)
+            assert ctx.info()["loop_mode"] == (1 if mode == "coop" else 0)
             st = ctx.block_lanczos(z["v0"][:N * n], stop_after=K, batch=3)
             assert st["iters"] == K and not st["stopped"]
             for k, g in (("v", "v"), ("tmp", "tmp"), ("Av", "Av"), ("p", "pblk")):
@@ -412,15 +414,15 @@ def test_persistent_loop_kernel_matches_oracle(lib, oracle, monkeypatch, n, p):
                                          not oracle.sparse_matrix_vector_product(Mp, want["v"], not right, n, p).any())
 
 
-def test_persistent_loop_kernel_is_the_default_for_small_problems(lib, monkeypatch):
+def test_persistent_loop_kernel_is_an_opt_in(lib, monkeypatch):
     monkeypatch.delenv("BLK_LOOP", raising=False)
     M = lib.synth.uniform_rows(2000, 1900, 20, seed=2)
+    with lib.BlockLanczos(M.reduced(P_FERMAT), n=4, prime=P_FERMAT) as ctx:             # default: CUDA graph (measured faster)
+        assert ctx.info()["loop_mode"] == 0
+    monkeypatch.setenv("BLK_LOOP", "coop")
     with lib.BlockLanczos(M.reduced(P_FERMAT), n=4, prime=P_FERMAT) as ctx:
         assert ctx.info()["loop_mode"] == 1
     with lib.BlockLanczos(M.reduced(P_FERMAT), n=4, prime=P_FERMAT, use_graph=0) as ctx:
         assert ctx.info()["loop_mode"] == 0
-    with lib.BlockLanczos(M.reduced(P_FERMAT), n=32, prime=P_FERMAT) as ctx:            # n_pad > 16: CUDA graph
-        assert ctx.info()["loop_mode"] == 0
-    monkeypatch.setenv("BLK_LOOP", "coop")
     with pytest.raises(lib.BlkError, match="BLK_LOOP=coop"):
         lib.BlockLanczos(M.reduced(P_FERMAT), n=32, prime=P_FERMAT)
