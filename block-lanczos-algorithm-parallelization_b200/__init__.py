@@ -55,7 +55,7 @@ class blk_info(C.Structure):
         ("local_M0", C.c_int64), ("local_M1", C.c_int64), ("nnz_local", C.c_int64 * 2),
         ("stored_local", C.c_int64 * 2), ("tiles", C.c_int64 * 2), ("n", C.c_int32), ("n_pad", C.c_int32),
         ("chunk_len", C.c_int32 * 2), ("groups_per_warp", C.c_int32), ("device_bytes", C.c_int64),
-        ("loop_mode", C.c_int32), ("reserved", C.c_int32),
+        ("loop_mode", C.c_int32), ("reserved", C.c_int32), ("bands", C.c_int32 * 2),
     ]
 
 

@@ -50,6 +50,13 @@ struct SpOp {
         // tiles [piece_tile[q], piece_tile[q+1]); after its fix-up, rows [piece_row[q], piece_row[q+1])
         // are final.  piece_scan[q] <= piece_tile[q] is the first tile whose open row ends in piece q.
         std::vector<int64_t> piece_tile, piece_row, piece_scan;
+        // Column bands (small n_pad, x block >> L2): the operator is ALSO stored as `bands.size()` operators over all rows, band b
+        // holding the entries whose column lies in [band_col[b], band_col[b+1]) -- a slice of x that stays L2-resident while its
+        // band runs, so its gathers hit L2 instead of pulling one 128-byte HBM line each.  Every band writes a partial
+        // result into zband (rows * n_pad words per band); k_band_combine adds them mod p.  launch_spmv dispatches here.
+        std::vector<SpOp> bands;
+        std::vector<int64_t> band_col;
+        u32 *zband = nullptr;
         u32 hot_cols = 0;          // > 0: entries carry a HOT bit (bit 30 of the column word): those x rows are gathered with
                                    // L2 evict_last, the rest evict_first (columns are then limited to 2^30)
 };

@@ -187,6 +187,7 @@ struct blk_ctx {
         static constexpr size_t STAGE_BYTES = 32u << 20;
         u32 *stage = nullptr;
         long long l2_persist_before = -1;       // cudaLimitPersistingL2CacheSize found at create time (restored on destroy)
+        int bands1 = 0, bands2 = 0;             // column bands of S1 / S2 (0: none), see SpOp::bands
         bool check = false;                     // BLK_CHECK=1: the n x n stage asserts the reference's correctness_tests
         int check_fault = 0;                    // BLK_CHECK_FAULT=k: corrupt vtAv in iteration k (tests the self-check)
         // Single-process multi-GPU job (blk_params.rank == BLK_RANK_ALL): this context owns one member context
@@ -1371,8 +1372,15 @@ int build_graph(blk_ctx *c)
 
 int kernels_per_iteration(const blk_ctx *c)
 {
-        // two products (+ their k_spmv_fix unless the rows crossing tiles are finished by look-back), dots, [small], orthogonalize
-        return (c->S1.lookback ? 1 : 2) + (c->S2.lookback ? 1 : 2) + 1 + (c->fuse_small ? 0 : 1) + 1;
+        // two products (+ their k_spmv_fix unless the rows crossing tiles are finished by look-back; banded products: every band
+        // plus the pass that adds the partial results), dots, [small], orthogonalize
+        auto product = [](const SpOp &op) {
+                if (op.bands.empty()) return op.lookback ? 1 : 2;
+                int k = 1;
+                for (const SpOp &b : op.bands) k += b.lookback ? 1 : 2;
+                return k;
+        };
+        return product(c->S1) + product(c->S2) + 1 + (c->fuse_small ? 0 : 1) + 1;
 }
 
 }  // namespace
@@ -1544,6 +1552,47 @@ void close_peers(blk_ctx *c)
         c->peer_tmp.clear(); c->peer_av.clear(); c->peer_ipc.clear();
 }
 
+// Column bands of one operator (SpOp::bands): the entries (rkey, ckey, val)[count] -- row keys global, in [lo, hi) -- are
+// split by column into K equal ranges and each range becomes an operator of its own over all rows.
+int build_bands(blk_ctx *c, SpOp *op, int K, int chunk_len, int64_t count, const int32_t *rkey, const int32_t *ckey, const u32 *val,
+                int64_t lo, int64_t hi, int64_t cols)
+{
+        if (K < 2 || hi <= lo || count <= 0) return 0;
+        std::vector<u32> hc;
+        if (count_dimension(c, count, ckey, cols, &hc)) return 1;
+        op->band_col.assign((size_t)K + 1, 0);
+        for (int b = 0; b <= K; b++) op->band_col[(size_t)b] = cols * b / K;
+        op->bands.assign((size_t)K, SpOp());
+        Scratch tmp;
+        unsigned long long *cnt = nullptr;
+        if (tmp.alloc(&cnt, sizeof(unsigned long long))) return 1;
+        for (int b = 0; b < K; b++) {
+                const int64_t c0 = op->band_col[(size_t)b], c1 = op->band_col[(size_t)b + 1];
+                int64_t sel = 0;
+                for (int64_t q = c0; q < c1; q++) sel += hc[(size_t)q];
+                Scratch buf;
+                int32_t *sr = nullptr, *sc = nullptr; u32 *sx = nullptr;
+                unsigned long long h = 0;
+                if (buf.alloc(&sr, sizeof(int32_t) * (size_t)sel) || buf.alloc(&sc, sizeof(int32_t) * (size_t)sel) || buf.alloc(&sx, sizeof(u32) * (size_t)sel))
+                        return 1;
+                CU(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
+                // (selection by column: the column array is the key, the row array rides along)
+                k_select_range<<<nb(count), 256, 0, c->stream>>>(count, ckey, rkey, val, c0, c1, sc, sr, sx, cnt, nullptr, 0, nullptr, 0);
+                CU(cudaMemcpyAsync(&h, cnt, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+                CU(cudaStreamSynchronize(c->stream));
+                if ((int64_t)h != sel) return fail("column band selection count mismatch");
+                std::string err = build_operator(&op->bands[(size_t)b], c->geo, chunk_len, hi - lo, cols, lo, sel, sr, sc, sx, c->m.p, nullptr, nullptr,
+                                                 1, c->stream, nullptr);
+                if (!err.empty()) return fail("column band: " + err);
+                op->bytes += op->bands[(size_t)b].bytes;
+        }
+        const size_t zb = sizeof(u32) * (size_t)K * (size_t)(hi - lo) * c->geo.np;
+        CU(cudaMalloc(&op->zband, zb));
+        CU(cudaMemsetAsync(op->zband, 0, zb, c->stream));
+        op->bytes += zb;
+        return 0;
+}
+
 // the multi-GPU part of blk_create: communicator, pieces, side stream, the recurrence blocks, the exchange mode
 int create_multi(blk_ctx *c, const blk_params *prm, bool grid_req)
 {
@@ -1609,7 +1658,7 @@ int create_multi(blk_ctx *c, const blk_params *prm, bool grid_req)
                 else if (!strcmp(ex, "push")) want = blk_ctx::XCH_PUSH;
                 else return fail("BLK_EXCHANGE must be nccl, ce or push");
         } else if (env_flag("BLK_P2P")) want = blk_ctx::XCH_CE;           // round-1 spelling
-        if (np < 4 || c->colblocks) want = blk_ctx::XCH_NCCL;          // rows shorter than 16 bytes / arrival-order mode
+        if (np < 4 || c->colblocks || c->bands1 > 1 || c->bands2 > 1) want = blk_ctx::XCH_NCCL;   // rows shorter than 16 bytes / arrival-order mode / banded products
         if (want != blk_ctx::XCH_NCCL) {
                 bool ok = false;
                 if (setup_peers(c, &ok)) return 1;
@@ -1708,6 +1757,29 @@ int create_impl(blk_ctx *c, const blk_params *prm)
                 }
         }
 
+        // ---- column bands (n_pad <= 4): with 4 ... 16-byte rows the x block is still far larger than L2 (config 4: 200 ... 800 MB)
+        // and every gather still costs a whole 128-byte HBM line -- 32 ... 8 times the bytes it uses.  Cutting the columns into
+        // bands whose slice of x stays in L2 turns those line fetches into L2 hits at the price of one partial result per band
+        // (rows * n_pad * 4 bytes written and read again), which is cheap exactly when n_pad is small.  BLK_BANDS=0 disables,
+        // BLK_BAND_BYTES sets the slice size.  Measured on the config-4 matrix (profiles/r02_column_bands.txt), ms per product:
+        // n = 1: 20.1 -> 6.6, n = 2: 26.8 -> 8.8, n = 4: 29.8 -> 15.9 with the default 48 MB (slices of 16 / 32 / 112 MB are slower).
+        {
+                const char *e = getenv("BLK_BANDS"), *eb = getenv("BLK_BAND_BYTES");
+                const long long band_bytes = eb ? std::max(4096ll, atoll(eb)) : 48ll << 20;
+                const long long min_bytes = 96ll << 20;
+                if (np <= 4 && !c->colblocks && !grid_req && !(e && e[0] == '0') && nnz > 0) {
+                        auto bands_for = [&](int64_t cols) -> int {
+                                const long long x_bytes = (long long)cols * np * 4;
+                                if (!eb && x_bytes <= min_bytes) return 0;           // fits L2 well enough as it is
+                                long long K = (x_bytes + band_bytes - 1) / band_bytes;
+                                return K < 2 ? 0 : (int)std::min(64ll, K);
+                        };
+                        c->bands1 = bands_for(c->N);          // S1 gathers rows of v
+                        c->bands2 = bands_for(c->Mc);         // S2 gathers rows of tmp
+                }
+        }
+        const bool banded = c->bands1 > 1 || c->bands2 > 1;
+
         // ---- degree-sorted labels for the N dimension + L2-resident hot prefix.  The rows of the Lanczos vectors can
         // be stored under any labels (dots are order-free, orthogonalize is row-wise); sorting them by decreasing
         // number of entries makes the rows product 1 gathers most often a contiguous prefix that L2 can keep.  With
@@ -1720,7 +1792,7 @@ int create_impl(blk_ctx *c, const blk_params *prm)
                 CU(cudaGetDeviceProperties(&prop, c->device));
                 long long min_bytes = emin ? atoll(emin) : 96ll << 20;
                 long long hot_bytes = eb ? atoll(eb) : 24ll << 20;
-                bool on = !c->colblocks && !grid_req && !(e && e[0] == '0') && np >= 4 && nnz > 0 && world <= HotCols::MAXB &&
+                bool on = !c->colblocks && !grid_req && !banded && !(e && e[0] == '0') && np >= 4 && nnz > 0 && world <= HotCols::MAXB &&
                           c->N < (1ll << 30) && (long long)c->N * np * 4 > min_bytes && hot_bytes > 0;
                 if (world > 1 && env_flag("BLK_HOT_SINGLE_ONLY")) on = false;       // A/B switch: round-1 behaviour
                 if (on) {
@@ -1756,6 +1828,7 @@ int create_impl(blk_ctx *c, const blk_params *prm)
                 want_pieces = e ? atoi(e) : (int)std::max(1ll, std::min(4ll, per_rank / 25000000ll));
                 if (want_pieces < 1) want_pieces = 1;
                 if (want_pieces > 32) want_pieces = 32;
+                if (banded) want_pieces = 1;          // banded products run whole (launch_spmv)
         }
         for (int which = 0; which < 2; which++) {
                 SpOp *op = which ? &c->S2 : &c->S1;
@@ -1767,6 +1840,7 @@ int create_impl(blk_ctx *c, const blk_params *prm)
                         err = build_operator(op, c->geo, prm->chunk_len, hi - lo, cols, lo, nnz, rk, ck, dx, m.p,
                                              which ? c->n_old2new : nullptr, which ? nullptr : c->n_old2new, 1, c->stream,
                                              which ? nullptr : &hot);
+                        if (err.empty() && build_bands(c, op, which ? c->bands2 : c->bands1, prm->chunk_len, nnz, rk, ck, dx, lo, hi, cols)) return 1;
                         if (err.empty() && c->colblocks &&
                             build_colops(c, which ? &c->cb2 : &c->cb1, c->colblocks, prm->chunk_len, nnz, rk, ck, dx, lo, hi, cols,
                                          which ? c->m_off : c->n_off))
@@ -1795,6 +1869,7 @@ int create_impl(blk_ctx *c, const blk_params *prm)
                         if ((int64_t)hcnt != sel) err = "shard selection count mismatch";
                         else err = build_operator(op, c->geo, prm->chunk_len, hi - lo, cols, lo, sel, sr, sc, sx, m.p, nullptr, nullptr,
                                                        want_pieces, c->stream, which ? nullptr : &hot);
+                        if (err.empty() && build_bands(c, op, which ? c->bands2 : c->bands1, prm->chunk_len, sel, sr, sc, sx, lo, hi, cols)) return 1;
                         if (err.empty() && c->colblocks &&
                             build_colops(c, which ? &c->cb2 : &c->cb1, c->colblocks, prm->chunk_len, sel, sr, sc, sx, lo, hi, cols,
                                          which ? c->m_off : c->n_off))
@@ -1846,7 +1921,7 @@ int create_impl(blk_ctx *c, const blk_params *prm)
                 if (e && !force && !off && strcmp(e, "auto")) return fail("BLK_LOOP must be graph, coop or auto");
                 const size_t working_set = c->S1.bytes + c->S2.bytes + c->block_bytes - 2 * blk_ctx::STAGE_BYTES;
                 const bool eligible = world == 1 && !c->colblocks && loop_coop_supported(np) && !c->S1.lookback && !c->S2.lookback &&
-                                      !c->S1.hot_cols && c->N > 0 && c->Mc > 0;
+                                      !c->S1.hot_cols && c->S1.bands.empty() && c->S2.bands.empty() && c->N > 0 && c->Mc > 0;
                 if (force && !eligible) return fail("BLK_LOOP=coop: the persistent loop kernel needs one GPU, n <= 16 and the default product kernels");
                 (void)working_set;
                 if (eligible && force) {
@@ -2695,6 +2770,7 @@ int blk_get_info(blk_ctx *c, blk_info *info)
         info->n = c->geo.n; info->n_pad = c->geo.np; info->groups_per_warp = c->geo.G;
         info->device_bytes = (int64_t)(c->S1.bytes + c->S2.bytes + c->block_bytes);
         info->loop_mode = (c->coop && c->use_graph != 0) ? 1 : 0;
+        info->bands[0] = (int32_t)c->S1.bands.size(); info->bands[1] = (int32_t)c->S2.bands.size();
         return 0;
 }
 

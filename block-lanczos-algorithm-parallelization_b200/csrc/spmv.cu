@@ -19,6 +19,7 @@
 // by k_spmv_fix when it completes it.  The exchange thus costs no extra kernel, no SMs of its own
 // and is spread evenly over the product -- this replaces the reference's per-iteration
 // Send/Recv + Gatherv of the product result (mpi/lanczos_modp.c:1108-1147).
+#include <algorithm>
 #include <cstdlib>
 #include "blk_internal.cuh"
 #include "spmv_body.cuh"
@@ -104,11 +105,61 @@ int launch_lv(const SpOp &op, const ModP &m, const u32 *x, u32 *y, const DevSmal
         return 2;
 }
 
+// y[e] = (z_0[e] + ... + z_{K-1}[e]) mod p: the partial results of the column bands of one product
+__global__ void __launch_bounds__(256)
+k_band_combine(u32 *__restrict__ y, const u32 *__restrict__ z, int K, size_t stride, int64_t count4, ModP m, const DevSmall *__restrict__ state)
+{
+        pdl_prologue();
+        if (state && state->halt) return;
+        // (stride and the blocks are multiples of 4 words whenever count4 > 0: rows * n_pad with n_pad = 4, or handled by the tail)
+        for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count4; e += (int64_t)gridDim.x * blockDim.x) {
+                u64 a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+                for (int q = 0; q < K; q++) {
+                        const uint4 t = __ldcs(reinterpret_cast<const uint4 *>(z + (size_t)q * stride) + e);
+                        a0 += t.x; a1 += t.y; a2 += t.z; a3 += t.w;
+                }
+                reinterpret_cast<uint4 *>(y)[e] = make_uint4(mp_reduce(a0, m), mp_reduce(a1, m), mp_reduce(a2, m), mp_reduce(a3, m));
+        }
+}
+__global__ void __launch_bounds__(256)
+k_band_combine1(u32 *__restrict__ y, const u32 *__restrict__ z, int K, size_t stride, int64_t first, int64_t count, ModP m,
+                const DevSmall *__restrict__ state)
+{
+        pdl_prologue();
+        if (state && state->halt) return;
+        for (int64_t e = first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x) {
+                u64 a = 0;
+                for (int q = 0; q < K; q++) a += z[(size_t)q * stride + e];
+                y[e] = mp_reduce(a, m);
+        }
+}
+
 }  // namespace
 
 int launch_spmv(const SpOp &op, const Geometry &geo, const ModP &m, const u32 *x, u32 *y,
                 const DevSmall *state, cudaStream_t st, int piece, const PushTargets *push)
 {
+        if (!op.bands.empty() && (piece < 0 || op.piece_tile.size() <= 2) && !(push && push->n > 0)) {
+                // column bands: K products whose x slices are L2-resident, then one pass that adds the partial results
+                const int K = (int)op.bands.size();
+                const size_t stride = (size_t)op.rows * geo.np;
+                int k = 0;
+                for (int b = 0; b < K; b++) k += launch_spmv(op.bands[b], geo, m, x, op.zband + (size_t)b * stride, state, st);
+                const int64_t count = (int64_t)stride;
+                const bool vec = (stride % 4) == 0 && ((uintptr_t)y % 16) == 0;
+                const int64_t count4 = vec ? count / 4 : 0;
+                if (count4 > 0) {
+                        unsigned blocks = (unsigned)std::min<int64_t>((int64_t)blk_sm_count() * 16, (count4 + 255) / 256);
+                        launch_k(k_band_combine, blocks, 256, 0, st, y, (const u32 *)op.zband, K, stride, count4, m, state);
+                        k++;
+                }
+                if (count4 * 4 < count) {
+                        unsigned blocks = (unsigned)std::min<int64_t>((int64_t)blk_sm_count() * 16, (count - count4 * 4 + 255) / 256);
+                        launch_k(k_band_combine1, blocks, 256, 0, st, y, (const u32 *)op.zband, K, stride, count4 * 4, count, m, state);
+                        k++;
+                }
+                return k;
+        }
         switch (geo.np) {
         case 1: return launch_lv<1, 1>(op, m, x, y, state, st, piece, push);
         case 2: return launch_lv<1, 2>(op, m, x, y, state, st, piece, push);

@@ -195,6 +195,7 @@ typedef struct blk_info {
         int32_t loop_mode;             /* how blk_iterate runs the loop: 0 chain of kernels / CUDA graph, 1 one persistent
                                           cooperative kernel (L2-resident problems on one GPU, BLK_LOOP) */
         int32_t reserved;
+        int32_t bands[2];              /* column bands of S1 / S2 (0: none): n_pad <= 4 with an x block far larger than L2 */
 } blk_info;
 int  blk_get_info(blk_ctx *ctx, blk_info *info);
 

@@ -27,6 +27,8 @@ MODES = {                      # environment of the exchange modes (DESIGN.md se
     "hot": {"BLK_HOT_MIN_BYTES": "0", "BLK_HOT_BYTES": "8192"},
     "hot_nccl": {"BLK_HOT_MIN_BYTES": "0", "BLK_HOT_BYTES": "8192", "BLK_EXCHANGE": "nccl"},
     # pieces pushed by the bulk-copy engine (k_push_bulk) instead of k_push_rows
+    # column-banded products (n_pad <= 4) forced on for the test-sized matrices: every rank's operators in bands
+    "bands": {"BLK_BAND_BYTES": "8192"},
     "bulk": {"BLK_PUSH_COPY": "bulk"},
     "bulk_kernel": {"BLK_PUSH_COPY": "bulk", "BLK_PUSH_AV": "kernel", "BLK_PUSH_CTAS": "3"},
 }
@@ -52,7 +54,7 @@ def test_sharded_run_matches_oracle(lib, world):
     _torchrun(world, 29500 + world, {})
 
 
-@pytest.mark.parametrize("mode", ["nccl", "push_kernel", "hot", "bulk_kernel"])
+@pytest.mark.parametrize("mode", ["nccl", "push_kernel", "hot", "bulk_kernel", "bands"])
 def test_exchange_modes_one_process_per_gpu(lib, mode):
     if _ngpus() < 2:
         pytest.skip("needs 2 GPUs")
@@ -68,7 +70,7 @@ def test_group_context_matches_oracle(lib, oracle, monkeypatch, world, mode):
         pytest.skip(f"needs {world} GPUs")
     if world > 2 and mode not in ("push", "nccl", "pieces8", "hot", "bulk"):
         pytest.skip("mode covered at world 2")
-    for k in ("BLK_EXCHANGE", "BLK_PUSH_AV", "BLK_RECUR", "BLK_PIECES", "BLK_HOT_MIN_BYTES", "BLK_HOT_BYTES", "BLK_PUSH_COPY", "BLK_PUSH_CTAS"):
+    for k in ("BLK_EXCHANGE", "BLK_PUSH_AV", "BLK_RECUR", "BLK_PIECES", "BLK_HOT_MIN_BYTES", "BLK_HOT_BYTES", "BLK_PUSH_COPY", "BLK_PUSH_CTAS", "BLK_BAND_BYTES"):
         monkeypatch.delenv(k, raising=False)
     for k, v in MODES[mode].items():
         monkeypatch.setenv(k, v)

@@ -426,3 +426,35 @@ def test_persistent_loop_kernel_is_an_opt_in(lib, monkeypatch):
         assert ctx.info()["loop_mode"] == 0
     with pytest.raises(lib.BlkError, match="BLK_LOOP=coop"):
         lib.BlockLanczos(M.reduced(P_FERMAT), n=32, prime=P_FERMAT)
+
+
+@pytest.mark.parametrize("n,p", [(1, P_FERMAT), (2, P_MERSENNE), (3, P_CAP), (4, P_MERSENNE), (4, 7)])
+@pytest.mark.parametrize("band_bytes", [4096, 1 << 16])
+def test_column_banded_products_match_oracle(lib, oracle, monkeypatch, n, p, band_bytes):
+    """n_pad <= 4 with an x block far larger than L2: the operators are also stored as column bands whose x slice stays
+    L2-resident, every band writes a partial result and k_band_combine adds them mod p (SpOp::bands, launch_spmv).
+    BLK_BAND_BYTES forces bands on test-sized matrices: products in both directions, whole runs (graph and chain) and the
+    state API against the oracle."""
+    monkeypatch.setenv("BLK_BAND_BYTES", str(band_bytes))
+    s = lib.synth
+    cases = [(s.powerlaw_rows(3000, 2700, mean=9, seed=3, with_empty_rows=11), False, 9),
+             (s.uniform_nnz(2500, 3100, 30000, seed=4, order="col"), True, -1),
+             (s.powerlaw_rows(1200, 1500, mean=7, seed=6, cap=900), False, 6),              # giant rows, Mc > N
+             (s.uniform_rows(7, 9, 2, seed=1), False, 3)]
+    rng = np.random.default_rng(1)
+    for ci, (M, right, stop_after) in enumerate(cases):
+        Mp = M.reduced(p)
+        N = M.ncols if right else M.nrows
+        for graph in (0, 1):
+            with lib.BlockLanczos(Mp, n=n, prime=p, right=right, use_graph=graph) as ctx:
+                if graph == 0:
+                    for tr in (False, True):
+                        cols = M.nrows if tr else M.ncols
+                        x = rng.integers(0, p, size=cols * n).astype(np.uint32)
+                        assert np.array_equal(ctx.sparse_matrix_vector_product(x, tr),
+                                              oracle.sparse_matrix_vector_product(Mp, x, tr, n, p)), (ci, n, tr)
+                got = ctx.block_lanczos(oracle.start_block(N * n, p), stop_after=stop_after, batch=4)
+            want = oracle.lanczos_run(Mp, n, p, right, stop_after=stop_after)
+            assert got["iters"] == want["iters"] and got["stopped"] == want["stopped"]
+            for k in ("v", "tmp", "Av", "p"):
+                assert np.array_equal(got[k], want[k]), (ci, n, graph, k)
