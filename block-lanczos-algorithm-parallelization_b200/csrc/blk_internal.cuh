@@ -54,9 +54,14 @@ struct SpOp {
         // holding the entries whose column lies in [band_col[b], band_col[b+1]) -- a slice of x that stays L2-resident while its
         // band runs, so its gathers hit L2 instead of pulling one 128-byte HBM line each.  Every band writes a partial
         // result into zband (rows * n_pad words per band); k_band_combine adds them mod p.  launch_spmv dispatches here.
+        // Two forms: (a) every band covers all rows and writes a partial result into zband (rows * n_pad words per band), added up
+        // by k_band_combine; (b) zband == nullptr: every band is a COMPACT operator over the rows that have entries in it (rowmap:
+        // its row r is row rowmap[r] of y) whose kernel ADDS its result to y, cleared beforehand -- no partial blocks, no dummy
+        // entries for rows that are empty inside a band.
         std::vector<SpOp> bands;
         std::vector<int64_t> band_col;
         u32 *zband = nullptr;
+        u32 *rowmap = nullptr;     // this operator is a compact band: output row r -> y row rowmap[r], results accumulate
         u32 hot_cols = 0;          // > 0: entries carry a HOT bit (bit 30 of the column word): those x rows are gathered with
                                    // L2 evict_last, the rest evict_first (columns are then limited to 2^30)
 };
@@ -165,6 +170,10 @@ std::string build_operator(SpOp *op, const Geometry &geo, int chunk_len, int64_t
                            const u32 *d_val, u32 prime, const u32 *row_map, const u32 *col_map, int pieces,
                            cudaStream_t st, const HotCols *hot = nullptr);
 void free_operator(SpOp *op);
+// Renumber the row keys of `count` entries (global keys in [row_lo, row_lo + rows)) to 0 .. R-1 over the rows that occur, in
+// increasing order; *rowmap_out (device, R words) maps the new numbers back to local rows (key - row_lo).
+std::string compact_rows(int64_t count, int32_t *d_row, int64_t row_lo, int64_t rows, u32 **rowmap_out, int64_t *nrows_out,
+                         cudaStream_t st);
 // old->new / new->old labels of one dimension sorted by decreasing number of entries; world > 1: the sorted
 // sequence is then dealt round-robin to `world` contiguous blocks (position s of the sorted order goes to block
 // s % world, place s / world), so that every block gets the same share of heavy rows -- equal rows, equal

@@ -188,6 +188,7 @@ struct blk_ctx {
         u32 *stage = nullptr;
         long long l2_persist_before = -1;       // cudaLimitPersistingL2CacheSize found at create time (restored on destroy)
         int bands1 = 0, bands2 = 0;             // column bands of S1 / S2 (0: none), see SpOp::bands
+        bool bands_acc = false;                 // BLK_BAND_ACC=1: compact accumulate-in-place bands (measured slower than partial results + combine)
         bool check = false;                     // BLK_CHECK=1: the n x n stage asserts the reference's correctness_tests
         int check_fault = 0;                    // BLK_CHECK_FAULT=k: corrupt vtAv in iteration k (tests the self-check)
         // Single-process multi-GPU job (blk_params.rank == BLK_RANK_ALL): this context owns one member context
@@ -1555,7 +1556,7 @@ void close_peers(blk_ctx *c)
 // Column bands of one operator (SpOp::bands): the entries (rkey, ckey, val)[count] -- row keys global, in [lo, hi) -- are
 // split by column into K equal ranges and each range becomes an operator of its own over all rows.
 int build_bands(blk_ctx *c, SpOp *op, int K, int chunk_len, int64_t count, const int32_t *rkey, const int32_t *ckey, const u32 *val,
-                int64_t lo, int64_t hi, int64_t cols)
+                int64_t lo, int64_t hi, int64_t cols, bool acc)
 {
         if (K < 2 || hi <= lo || count <= 0) return 0;
         std::vector<u32> hc;
@@ -1581,11 +1582,25 @@ int build_bands(blk_ctx *c, SpOp *op, int K, int chunk_len, int64_t count, const
                 CU(cudaMemcpyAsync(&h, cnt, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
                 CU(cudaStreamSynchronize(c->stream));
                 if ((int64_t)h != sel) return fail("column band selection count mismatch");
-                std::string err = build_operator(&op->bands[(size_t)b], c->geo, chunk_len, hi - lo, cols, lo, sel, sr, sc, sx, c->m.p, nullptr, nullptr,
-                                                 1, c->stream, nullptr);
-                if (!err.empty()) return fail("column band: " + err);
+                std::string err;
+                if (acc) {
+                        // compact form: only the rows that have entries in this band, results accumulated into y
+                        u32 *rowmap = nullptr;
+                        int64_t nrows = 0;
+                        err = compact_rows(sel, sr, lo, hi - lo, &rowmap, &nrows, c->stream);
+                        if (err.empty()) err = build_operator(&op->bands[(size_t)b], c->geo, chunk_len, nrows, cols, 0, sel, sr, sc, sx, c->m.p, nullptr,
+                                                              nullptr, 1, c->stream, nullptr);
+                        if (!err.empty()) { cudaFree(rowmap); return fail("column band: " + err); }
+                        op->bands[(size_t)b].rowmap = rowmap;
+                        op->bands[(size_t)b].bytes += sizeof(u32) * (size_t)nrows;
+                } else {
+                        err = build_operator(&op->bands[(size_t)b], c->geo, chunk_len, hi - lo, cols, lo, sel, sr, sc, sx, c->m.p, nullptr, nullptr,
+                                             1, c->stream, nullptr);
+                        if (!err.empty()) return fail("column band: " + err);
+                }
                 op->bytes += op->bands[(size_t)b].bytes;
         }
+        if (acc) return 0;
         const size_t zb = sizeof(u32) * (size_t)K * (size_t)(hi - lo) * c->geo.np;
         CU(cudaMalloc(&op->zband, zb));
         CU(cudaMemsetAsync(op->zband, 0, zb, c->stream));
@@ -1767,7 +1782,12 @@ int create_impl(blk_ctx *c, const blk_params *prm)
                 const char *e = getenv("BLK_BANDS"), *eb = getenv("BLK_BAND_BYTES");
                 const long long band_bytes = eb ? std::max(4096ll, atoll(eb)) : 48ll << 20;
                 const long long min_bytes = 96ll << 20;
-                if (np <= 4 && !c->colblocks && !grid_req && !(e && e[0] == '0') && nnz > 0) {
+                if (const char *ea = getenv("BLK_BAND_ACC")) c->bands_acc = ea[0] != '0';
+                // (the partial-result form pays rows * n_pad * 8 bytes per band: only for n_pad <= 4.  The accumulate form -- compact
+                // bands that add into y, allowed up to n_pad = 8 -- avoids the partial blocks and the dummy entries but its
+                // read-modify-write of scattered y rows costs a line per row again: 8.6 / 13.0 / 20.8 ms against 6.6 / 8.8 / 15.9 for
+                // n = 1 / 2 / 4 and 39.9 against 31.5 ms unbanded at n = 8, profiles/r02_column_bands.txt; it stays an opt-in)
+                if (np <= (c->bands_acc ? 8 : 4) && !c->colblocks && !grid_req && !(e && e[0] == '0') && nnz > 0) {
                         auto bands_for = [&](int64_t cols) -> int {
                                 const long long x_bytes = (long long)cols * np * 4;
                                 if (!eb && x_bytes <= min_bytes) return 0;           // fits L2 well enough as it is
@@ -1840,7 +1860,7 @@ int create_impl(blk_ctx *c, const blk_params *prm)
                         err = build_operator(op, c->geo, prm->chunk_len, hi - lo, cols, lo, nnz, rk, ck, dx, m.p,
                                              which ? c->n_old2new : nullptr, which ? nullptr : c->n_old2new, 1, c->stream,
                                              which ? nullptr : &hot);
-                        if (err.empty() && build_bands(c, op, which ? c->bands2 : c->bands1, prm->chunk_len, nnz, rk, ck, dx, lo, hi, cols)) return 1;
+                        if (err.empty() && build_bands(c, op, which ? c->bands2 : c->bands1, prm->chunk_len, nnz, rk, ck, dx, lo, hi, cols, c->bands_acc)) return 1;
                         if (err.empty() && c->colblocks &&
                             build_colops(c, which ? &c->cb2 : &c->cb1, c->colblocks, prm->chunk_len, nnz, rk, ck, dx, lo, hi, cols,
                                          which ? c->m_off : c->n_off))
@@ -1869,7 +1889,7 @@ int create_impl(blk_ctx *c, const blk_params *prm)
                         if ((int64_t)hcnt != sel) err = "shard selection count mismatch";
                         else err = build_operator(op, c->geo, prm->chunk_len, hi - lo, cols, lo, sel, sr, sc, sx, m.p, nullptr, nullptr,
                                                        want_pieces, c->stream, which ? nullptr : &hot);
-                        if (err.empty() && build_bands(c, op, which ? c->bands2 : c->bands1, prm->chunk_len, sel, sr, sc, sx, lo, hi, cols)) return 1;
+                        if (err.empty() && build_bands(c, op, which ? c->bands2 : c->bands1, prm->chunk_len, sel, sr, sc, sx, lo, hi, cols, c->bands_acc)) return 1;
                         if (err.empty() && c->colblocks &&
                             build_colops(c, which ? &c->cb2 : &c->cb1, c->colblocks, prm->chunk_len, sel, sr, sc, sx, lo, hi, cols,
                                          which ? c->m_off : c->n_off))

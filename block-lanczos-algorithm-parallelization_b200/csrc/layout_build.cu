@@ -144,8 +144,66 @@ void free_operator(SpOp *op)
         cudaFree(op->ent); cudaFree(op->chunk_row); cudaFree(op->tail_row);
         cudaFree(op->span); cudaFree(op->whead); cudaFree(op->back); cudaFree(op->ready);
         for (auto &b : op->bands) free_operator(&b);
-        cudaFree(op->zband);
+        cudaFree(op->zband); cudaFree(op->rowmap);
         *op = SpOp();
+}
+
+namespace {
+__global__ void k_mark_rows(int64_t count, const int32_t *__restrict__ row, int64_t row_lo, u32 *__restrict__ flag)
+{
+        int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (s < count) flag[(int64_t)row[s] - row_lo] = 1u;
+}
+__global__ void k_renumber_rows(int64_t count, int32_t *__restrict__ row, int64_t row_lo, const u32 *__restrict__ idx)
+{
+        int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (s < count) row[s] = (int32_t)idx[(int64_t)row[s] - row_lo];
+}
+__global__ void k_fill_rowmap(int64_t rows, const u32 *__restrict__ flag, const u32 *__restrict__ idx, u32 *__restrict__ rowmap)
+{
+        int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (r < rows && flag[r]) rowmap[idx[r]] = (u32)r;
+}
+}  // namespace
+
+std::string compact_rows(int64_t count, int32_t *d_row, int64_t row_lo, int64_t rows, u32 **rowmap_out, int64_t *nrows_out,
+                         cudaStream_t st)
+{
+        *rowmap_out = nullptr; *nrows_out = 0;
+        if (count <= 0 || rows <= 0) return "";
+        u32 *flag = nullptr, *idx = nullptr;
+        void *tmp = nullptr;
+        auto cleanup = [&]() { cudaFree(flag); cudaFree(idx); cudaFree(tmp); };
+#define CKR(call)                                                                                  \
+        do {                                                                                       \
+                cudaError_t e_ = (call);                                                           \
+                if (e_ != cudaSuccess) {                                                           \
+                        std::string err = std::string(#call) + ": " + cudaGetErrorString(e_);      \
+                        cleanup(); cudaFree(*rowmap_out); *rowmap_out = nullptr;                   \
+                        return err;                                                                \
+                }                                                                                  \
+        } while (0)
+        CKR(cudaMalloc(&flag, sizeof(u32) * (size_t)(rows + 1)));
+        CKR(cudaMalloc(&idx, sizeof(u32) * (size_t)(rows + 1)));
+        CKR(cudaMemsetAsync(flag, 0, sizeof(u32) * (size_t)(rows + 1), st));
+        k_mark_rows<<<nblk(count), TB, 0, st>>>(count, d_row, row_lo, flag);
+        CKR(cudaGetLastError());
+        size_t tb = 0;
+        CKR(cub::DeviceScan::ExclusiveSum(nullptr, tb, flag, idx, rows + 1, st));
+        CKR(cudaMalloc(&tmp, tb ? tb : 16));
+        CKR(cub::DeviceScan::ExclusiveSum(tmp, tb, flag, idx, rows + 1, st));
+        u32 h = 0;
+        CKR(cudaMemcpyAsync(&h, idx + rows, sizeof(u32), cudaMemcpyDeviceToHost, st));
+        CKR(cudaStreamSynchronize(st));
+        *nrows_out = (int64_t)h;
+        CKR(cudaMalloc(rowmap_out, sizeof(u32) * (size_t)(h ? h : 1)));
+        k_renumber_rows<<<nblk(count), TB, 0, st>>>(count, d_row, row_lo, idx);
+        k_fill_rowmap<<<nblk(rows), TB, 0, st>>>(rows, flag, idx, *rowmap_out);
+        CKR(cudaGetLastError());
+        CKR(cudaStreamSynchronize(st));
+        cleanup();
+        return "";
+#undef CKR
 }
 
 static int pick_chunk_len(int64_t stored, int G)

@@ -29,11 +29,12 @@ namespace {
 constexpr int WARPS = 8;     // warps (tiles) per thread block
 
 // back / ready (nullable together): complete the rows that cross tile borders by look-back (see SpOp)
-template <int L, int V, int FOLD, int HOT, int PUSH>
+template <int L, int V, int FOLD, int HOT, int PUSH, int ACC = 0>
 __global__ void __launch_bounds__(WARPS * 32)
 k_spmv(const uint2 *__restrict__ ent, const u32 *__restrict__ chunk_row, u32 *__restrict__ whead,
        int64_t tile0, int64_t ntiles, int Q, u32 rows, const u32 *__restrict__ x, u32 *__restrict__ y, ModP m,
-       const DevSmall *__restrict__ state, u32 hot, PushTargets push, const u32 *__restrict__ back, u32 *__restrict__ ready)
+       const DevSmall *__restrict__ state, u32 hot, PushTargets push, const u32 *__restrict__ back, u32 *__restrict__ ready,
+       const u32 *__restrict__ rowmap)
 {
         pdl_prologue();
         u64 pol_hot = 0, pol_cold = 0;
@@ -45,7 +46,7 @@ k_spmv(const uint2 *__restrict__ ent, const u32 *__restrict__ chunk_row, u32 *__
         const int lane = threadIdx.x & 31;
         const int64_t t = tile0 + (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);      // tiles [tile0, ntiles)
         if (t >= ntiles) return;
-        spmv_tile<L, V, FOLD, HOT, PUSH, 0>(ent, chunk_row, whead, t, Q, rows, x, y, m, pol_hot, pol_cold, push, back, ready, lane);
+        spmv_tile<L, V, FOLD, HOT, PUSH, 0, ACC>(ent, chunk_row, whead, t, Q, rows, x, y, m, pol_hot, pol_cold, push, back, ready, lane, rowmap);
 }
 
 // rows that cross tile borders: y[row] (partial left by the tile where the row starts) plus the
@@ -54,7 +55,7 @@ template <int L, int V>
 __global__ void __launch_bounds__(256)
 k_spmv_fix(const u32 *__restrict__ tail_row, const u32 *__restrict__ span, const u32 *__restrict__ whead,
            int64_t scan_lo, int64_t tile_lo, int64_t tile_hi, u32 *__restrict__ y, ModP m,
-           const DevSmall *__restrict__ state, PushTargets push)
+           const DevSmall *__restrict__ state, PushTargets push, const u32 *__restrict__ rowmap)
 {
         pdl_prologue();
         // finishes the rows that END in tiles [tile_lo, tile_hi); such a row starts in a tile >= scan_lo
@@ -63,7 +64,7 @@ k_spmv_fix(const u32 *__restrict__ tail_row, const u32 *__restrict__ span, const
         int64_t gid = scan_lo + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / L;
         int sub = threadIdx.x % L;
         if (gid >= tile_hi) return;
-        spmv_fix_row<L, V, 0>(tail_row, span, whead, gid, sub, tile_lo, tile_hi, y, m, push);
+        spmv_fix_row<L, V, 0>(tail_row, span, whead, gid, sub, tile_lo, tile_hi, y, m, push, rowmap);
 }
 
 template <int L, int V, int HOT, int PUSH>
@@ -75,9 +76,23 @@ void launch_hot(const SpOp &op, const ModP &m, const u32 *x, u32 *y, const DevSm
         const u32 *back = op.lookback ? op.back : nullptr;
         u32 *ready = op.lookback ? op.ready : nullptr;
         switch (m.fold_every) {
-        case 0: launch_k(k_spmv<L, V, 0, HOT, PUSH>, blocks, WARPS * 32, 0, st, op.ent, op.chunk_row, op.whead, t0, t1, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols, push, back, ready); break;
-        case 8: launch_k(k_spmv<L, V, 8, HOT, PUSH>, blocks, WARPS * 32, 0, st, op.ent, op.chunk_row, op.whead, t0, t1, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols, push, back, ready); break;
-        default: launch_k(k_spmv<L, V, 2, HOT, PUSH>, blocks, WARPS * 32, 0, st, op.ent, op.chunk_row, op.whead, t0, t1, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols, push, back, ready); break;
+        case 0: launch_k(k_spmv<L, V, 0, HOT, PUSH>, blocks, WARPS * 32, 0, st, op.ent, op.chunk_row, op.whead, t0, t1, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols, push, back, ready, (const u32 *)nullptr); break;
+        case 8: launch_k(k_spmv<L, V, 8, HOT, PUSH>, blocks, WARPS * 32, 0, st, op.ent, op.chunk_row, op.whead, t0, t1, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols, push, back, ready, (const u32 *)nullptr); break;
+        default: launch_k(k_spmv<L, V, 2, HOT, PUSH>, blocks, WARPS * 32, 0, st, op.ent, op.chunk_row, op.whead, t0, t1, op.Q, (u32)op.rows, x, y, m, state, op.hot_cols, push, back, ready, (const u32 *)nullptr); break;
+        }
+}
+
+// compact column-band operator (SpOp::rowmap): results are added into y[rowmap[row]]
+template <int L, int V>
+void launch_acc(const SpOp &op, const ModP &m, const u32 *x, u32 *y, const DevSmall *state, cudaStream_t st)
+{
+        unsigned blocks = (unsigned)((op.ntiles + WARPS - 1) / WARPS);
+        if (blocks == 0) return;
+        const PushTargets none;
+        switch (m.fold_every) {
+        case 0: launch_k(k_spmv<L, V, 0, 0, 0, 1>, blocks, WARPS * 32, 0, st, op.ent, op.chunk_row, op.whead, (int64_t)0, op.ntiles, op.Q, (u32)op.rows, x, y, m, state, 0u, none, (const u32 *)nullptr, (u32 *)nullptr, (const u32 *)op.rowmap); break;
+        case 8: launch_k(k_spmv<L, V, 8, 0, 0, 1>, blocks, WARPS * 32, 0, st, op.ent, op.chunk_row, op.whead, (int64_t)0, op.ntiles, op.Q, (u32)op.rows, x, y, m, state, 0u, none, (const u32 *)nullptr, (u32 *)nullptr, (const u32 *)op.rowmap); break;
+        default: launch_k(k_spmv<L, V, 2, 0, 0, 1>, blocks, WARPS * 32, 0, st, op.ent, op.chunk_row, op.whead, (int64_t)0, op.ntiles, op.Q, (u32)op.rows, x, y, m, state, 0u, none, (const u32 *)nullptr, (u32 *)nullptr, (const u32 *)op.rowmap); break;
         }
 }
 
@@ -86,6 +101,13 @@ int launch_lv(const SpOp &op, const ModP &m, const u32 *x, u32 *y, const DevSmal
               const PushTargets *push)
 {
         if (op.rows <= 0) return 0;                    // an empty shard (more ranks than rows): nothing to produce
+        if (op.rowmap) {
+                launch_acc<L, V>(op, m, x, y, state, st);
+                if (op.crossing)
+                        launch_k(k_spmv_fix<L, V>, (unsigned)((op.ntiles * L + 255) / 256), 256, 0, st, op.tail_row, op.span, op.whead, (int64_t)0, (int64_t)0,
+                                 op.ntiles, y, m, state, PushTargets(), (const u32 *)op.rowmap);
+                return op.crossing ? 2 : 1;
+        }
         int64_t t0 = 0, t1 = op.ntiles, scan = 0;
         if (piece >= 0) { t0 = op.piece_tile[piece]; t1 = op.piece_tile[piece + 1]; scan = op.piece_scan[piece]; }
         const PushTargets none;
@@ -101,8 +123,17 @@ int launch_lv(const SpOp &op, const ModP &m, const u32 *x, u32 *y, const DevSmal
         int64_t threads = (t1 - scan) * L;
         if (threads > 0)
                 launch_k(k_spmv_fix<L, V>, (unsigned)((threads + 255) / 256), 256, 0, st, op.tail_row, op.span, op.whead, scan, t0, t1, y, m, state,
-                                                                                   push ? *push : none);
+                                                                                   push ? *push : none, (const u32 *)nullptr);
         return 2;
+}
+
+// y <- 0 ahead of accumulate-in-place bands (a kernel, not a memset: a halted iteration must leave y alone)
+__global__ void __launch_bounds__(256)
+k_zero_block(u32 *__restrict__ y, int64_t count, const DevSmall *__restrict__ state)
+{
+        pdl_prologue();
+        if (state && state->halt) return;
+        for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x) y[e] = 0u;
 }
 
 // y[e] = (z_0[e] + ... + z_{K-1}[e]) mod p: the partial results of the column bands of one product
@@ -144,6 +175,13 @@ int launch_spmv(const SpOp &op, const Geometry &geo, const ModP &m, const u32 *x
                 const int K = (int)op.bands.size();
                 const size_t stride = (size_t)op.rows * geo.np;
                 int k = 0;
+                if (!op.zband) {
+                        // accumulate-in-place bands over their non-empty rows: clear y, then every band adds its part
+                        unsigned blocks = (unsigned)std::min<int64_t>((int64_t)blk_sm_count() * 16, ((int64_t)stride + 255) / 256);
+                        if (blocks) { launch_k(k_zero_block, blocks, 256, 0, st, y, (int64_t)stride, state); k++; }
+                        for (int b = 0; b < K; b++) k += launch_spmv(op.bands[b], geo, m, x, y, state, st);
+                        return k;
+                }
                 for (int b = 0; b < K; b++) k += launch_spmv(op.bands[b], geo, m, x, op.zband + (size_t)b * stride, state, st);
                 const int64_t count = (int64_t)stride;
                 const bool vec = (stride % 4) == 0 && ((uintptr_t)y % 16) == 0;

@@ -63,13 +63,31 @@ __device__ __forceinline__ u32 ld_acquire(const u32 *p)
         return v;
 }
 
+// Store of a finished (or partial) output row.  ACC = 1 (compact column-band operators, SpOp::rowmap): output row `row` of the
+// operator is row rowmap[row] of y and the result is ADDED to what y holds -- no other warp of the launch touches that row.
+template <int V, int ACC>
+__device__ __forceinline__ void store_row(u32 *ys, const u32 *__restrict__ rowmap, const u32 row, const int np, const u32 (&r)[V], const ModP &m)
+{
+        if (ACC) {
+                u32 *dst = ys + (size_t)__ldg(rowmap + row) * np;
+                u32 old[V], o[V];
+                load_vec_rw<V>(old, dst);
+#pragma unroll
+                for (int k = 0; k < V; k++) o[k] = mp_add(old[k], r[k], m);
+                store_vec<V>(dst, o);
+        } else {
+                store_vec<V>(ys + (size_t)row * np, r);
+        }
+}
+
 // One tile (one warp): lane-group g walks chunk g of tile t.  back / ready (nullable together): complete the
 // rows that cross tile borders by look-back (see SpOp).
-template <int L, int V, int FOLD, int HOT, int PUSH, int COH>
+template <int L, int V, int FOLD, int HOT, int PUSH, int COH, int ACC = 0>
 __device__ __forceinline__ void spmv_tile(const uint2 *__restrict__ ent, const u32 *__restrict__ chunk_row, u32 *whead,
                                           const int64_t t, const int Q, const u32 rows, const u32 *x, u32 *y, const ModP &m,
                                           const u64 pol_hot, const u64 pol_cold, const PushTargets &push,
-                                          const u32 *__restrict__ back, u32 *ready, const int lane)
+                                          const u32 *__restrict__ back, u32 *ready, const int lane,
+                                          const u32 *__restrict__ rowmap = nullptr)
 {
         constexpr int G = 32 / L;
         constexpr int NP = L * V;
@@ -123,7 +141,7 @@ __device__ __forceinline__ void spmv_tile(const uint2 *__restrict__ ent, const u
                                         head_type = 1;
                                         head_open = false;
                                 } else {
-                                        store_vec<V>(ys + (size_t)row * NP, r);
+                                        store_row<V, ACC>(ys, rowmap, row, NP, r, m);
                                 }
                                 row++;
                                 pending = false;
@@ -171,7 +189,7 @@ __device__ __forceinline__ void spmv_tile(const uint2 *__restrict__ ent, const u
                 u32 o[V];
 #pragma unroll
                 for (int k = 0; k < V; k++) o[k] = (g < G - 1) ? mp_add(tailv[k], nx[k], m) : tailv[k];
-                store_vec<V>(ys + (size_t)row * NP, o);
+                store_row<V, ACC>(ys, rowmap, row, NP, o, m);
         }
         if (g == 0 && head_type != 0) store_vec<V>(whead + t * NP + sub * V, headv);
 
@@ -252,13 +270,14 @@ __device__ __forceinline__ void spmv_tile(const uint2 *__restrict__ ent, const u
 template <int L, int V, int COH>
 __device__ __forceinline__ void spmv_fix_row(const u32 *__restrict__ tail_row, const u32 *__restrict__ span, const u32 *whead,
                                              const int64_t gid, const int sub, const int64_t tile_lo, const int64_t tile_hi,
-                                             u32 *y, const ModP &m, const PushTargets &push)
+                                             u32 *y, const ModP &m, const PushTargets &push, const u32 *__restrict__ rowmap = nullptr)
 {
         constexpr int NP = L * V;
         u32 sp = __ldg(span + gid);
         if (sp == 0) return;
         if (gid + sp >= tile_hi || gid + sp < tile_lo) return;      // ends in a later / an earlier piece
         u32 r = __ldg(tail_row + gid);
+        if (rowmap) r = __ldg(rowmap + r);          // compact band operator: the partial row lives (accumulated) in y[rowmap[r]]
         u32 cur[V];
         if (COH) load_vec_cg<V>(cur, y + (size_t)r * NP + sub * V);
         else load_vec_rw<V>(cur, y + (size_t)r * NP + sub * V);

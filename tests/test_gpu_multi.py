@@ -70,7 +70,7 @@ def test_group_context_matches_oracle(lib, oracle, monkeypatch, world, mode):
         pytest.skip(f"needs {world} GPUs")
     if world > 2 and mode not in ("push", "nccl", "pieces8", "hot", "bulk"):
         pytest.skip("mode covered at world 2")
-    for k in ("BLK_EXCHANGE", "BLK_PUSH_AV", "BLK_RECUR", "BLK_PIECES", "BLK_HOT_MIN_BYTES", "BLK_HOT_BYTES", "BLK_PUSH_COPY", "BLK_PUSH_CTAS", "BLK_BAND_BYTES"):
+    for k in ("BLK_EXCHANGE", "BLK_PUSH_AV", "BLK_RECUR", "BLK_PIECES", "BLK_HOT_MIN_BYTES", "BLK_HOT_BYTES", "BLK_PUSH_COPY", "BLK_PUSH_CTAS", "BLK_BAND_BYTES", "BLK_BAND_ACC"):
         monkeypatch.delenv(k, raising=False)
     for k, v in MODES[mode].items():
         monkeypatch.setenv(k, v)

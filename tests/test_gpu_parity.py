@@ -428,14 +428,21 @@ def test_persistent_loop_kernel_is_an_opt_in(lib, monkeypatch):
         lib.BlockLanczos(M.reduced(P_FERMAT), n=32, prime=P_FERMAT)
 
 
-@pytest.mark.parametrize("n,p", [(1, P_FERMAT), (2, P_MERSENNE), (3, P_CAP), (4, P_MERSENNE), (4, 7)])
+@pytest.mark.parametrize("n,p", [(1, P_FERMAT), (2, P_MERSENNE), (3, P_CAP), (4, P_MERSENNE), (4, 7), (8, P_MERSENNE), (6, P_FERMAT)])
 @pytest.mark.parametrize("band_bytes", [4096, 1 << 16])
-def test_column_banded_products_match_oracle(lib, oracle, monkeypatch, n, p, band_bytes):
-    """n_pad <= 4 with an x block far larger than L2: the operators are also stored as column bands whose x slice stays
-    L2-resident, every band writes a partial result and k_band_combine adds them mod p (SpOp::bands, launch_spmv).
-    BLK_BAND_BYTES forces bands on test-sized matrices: products in both directions, whole runs (graph and chain) and the
-    state API against the oracle."""
+@pytest.mark.parametrize("acc", [1, 0])
+def test_column_banded_products_match_oracle(lib, oracle, monkeypatch, n, p, band_bytes, acc):
+    """Small n_pad with an x block far larger than L2: the operators are also stored as column bands whose x slice stays
+    L2-resident (SpOp::bands, launch_spmv).  acc = 0 (default, n_pad <= 4): every band writes a partial result and
+    k_band_combine adds them mod p; acc = 1 (BLK_BAND_ACC=1, n_pad <= 8; measured slower): every band is a compact operator
+    over its non-empty rows whose kernel adds its result into y.  BLK_BAND_BYTES forces bands on test-sized matrices: products in both directions, whole runs (graph and
+    chain) and the state API against the oracle."""
+    if not acc and n > 4:
+        pytest.skip("the partial-result form serves n_pad <= 4")
+    if acc and band_bytes != 4096:
+        pytest.skip("the opt-in accumulate form is covered at the small slice size")
     monkeypatch.setenv("BLK_BAND_BYTES", str(band_bytes))
+    monkeypatch.setenv("BLK_BAND_ACC", str(acc))
     s = lib.synth
     cases = [(s.powerlaw_rows(3000, 2700, mean=9, seed=3, with_empty_rows=11), False, 9),
              (s.uniform_nnz(2500, 3100, 30000, seed=4, order="col"), True, -1),
@@ -447,6 +454,9 @@ def test_column_banded_products_match_oracle(lib, oracle, monkeypatch, n, p, ban
         N = M.ncols if right else M.nrows
         for graph in (0, 1):
             with lib.BlockLanczos(Mp, n=n, prime=p, right=right, use_graph=graph) as ctx:
+                np_ = 1 << (n - 1).bit_length()
+                if min(M.nrows, M.ncols) * np_ * 4 >= 2 * band_bytes:
+                    assert min(ctx.info()["bands"]) >= 2
                 if graph == 0:
                     for tr in (False, True):
                         cols = M.nrows if tr else M.ncols

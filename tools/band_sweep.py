@@ -12,17 +12,17 @@ rows, cols, vals, nnz = bench.gen_device_coo(torch, w, dev)
 torch.cuda.synchronize()
 coo = (w["rows"], w["cols"], nnz, rows.data_ptr(), cols.data_ptr(), vals.data_ptr())
 out = []
-settings = [("64MB", {"BLK_BAND_BYTES": str(64 << 20)}), ("80MB", {"BLK_BAND_BYTES": str(80 << 20)}), ("112MB", {"BLK_BAND_BYTES": str(112 << 20)})]
-for n in (1, 2, 4):
+settings = [("acc48MB", {}), ("acc64MB", {"BLK_BAND_BYTES": str(64 << 20)}), ("acc32MB", {"BLK_BAND_BYTES": str(32 << 20)}), ("partial48MB", {"BLK_BAND_ACC": "0"})]
+for n in (1, 2, 4, 8):
     for name, env in settings:
-        for k in ("BLK_BANDS", "BLK_BAND_BYTES"):
+        for k in ("BLK_BANDS", "BLK_BAND_BYTES", "BLK_BAND_ACC"):
             os.environ.pop(k, None)
         os.environ.update(env)
         t0 = time.time()
         ctx = B.BlockLanczos(n=n, prime=2147483647, right=False, device=0, device_coo=coo)
         torch.cuda.synchronize()
         build = time.time() - t0
-        rec = {"n": n, "bands": name, "build_s": round(build, 2), "device_gb": round(ctx.info()["device_bytes"] / 1e9, 1)}
+        rec = {"n": n, "bands": name, "K": ctx.info()["bands"], "build_s": round(build, 2), "device_gb": round(ctx.info()["device_bytes"] / 1e9, 1)}
         for tr in (False, True):
             rec["Mt_x" if tr else "M_x"] = round(ctx.time_spmv(tr, 3), 3)
         ctx.close()
