@@ -9,10 +9,13 @@ the kernels; this file is the specification they implement, small enough to read
   * a group stores the rows that start AND end inside its chunk; the piece of a row it inherits (head) and the row
     it leaves unfinished (tail) are stitched inside the warp by a suffix scan over the groups; what crosses tile
     borders goes through whead[tile] and is finished either by k_spmv_fix using tail_row[tile] and span[tile]
-    (BLK_SPMV_FIX=kernel), or -- the default -- inside k_spmv by look-back: the tile in which the row ENDS
+    (the default: measured faster), or -- BLK_SPMV_FIX=lookback -- inside k_spmv by look-back: the tile in which the row ENDS
     (back[tile] = number of tiles back to the one where it started) waits for the `ready` flags of those tiles,
     adds the partial row the first one left in y, the whead of the ones in between and its own head, and clears
-    the flags again.
+    the flags again;
+  * column bands (SpOp::bands, small n_pad): the operator cut into K column ranges, each an ordinary chunk stream; either every
+    band covers all rows and the K partial results are added mod p (k_band_combine), or every band is a compact stream over
+    its non-empty rows (rowmap) whose results are added into a cleared y.
 """
 import numpy as np
 import pytest
@@ -189,3 +192,39 @@ def test_chunk_stream_model_matches_oracle(lib, oracle, Q, G):
             mem = np.empty_like(perm); mem[perm] = np.arange(perm.size)                   # stream position -> memory position
             where = [mem[(t * G + g) * Q + i] for g in range(G)]
             assert where == list(range(where[0], where[0] + G))
+
+
+@pytest.mark.parametrize("K", [2, 3, 7])
+def test_column_band_model_matches_oracle(lib, oracle, K):
+    """csrc/context.cu build_bands + csrc/spmv.cu launch_spmv: both forms of the banded product."""
+    p, n, Q, G = 2147483647, 2, 8, 4
+    rng = np.random.default_rng(K)
+    for name, M in matrices(lib).items():
+        Mp = M.reduced(p)
+        for transpose in (False, True):
+            rows, cols = (M.ncols, M.nrows) if transpose else (M.nrows, M.ncols)
+            ri, ci = (Mp.j, Mp.i) if transpose else (Mp.i, Mp.j)
+            x = rng.integers(0, p, size=cols * n).astype(np.uint32)
+            want = oracle.sparse_matrix_vector_product(Mp, x, transpose, n, p)
+            band_col = [cols * b // K for b in range(K + 1)]
+            partial = np.zeros((K, rows * n), dtype=np.uint64)
+            acc = np.zeros((rows, n), dtype=np.uint64)                           # k_zero_block
+            seen = 0
+            for b in range(K):
+                sel = (ci >= band_col[b]) & (ci < band_col[b + 1])
+                seen += int(sel.sum())
+                # form (a): the band over all rows (rows without entries in it get a dummy entry and produce zero)
+                band = lib.SparseCOO(rows, cols, ri[sel], ci[sel], Mp.x[sel])
+                partial[b] = ChunkStream(band, False, Q, G).spmv(x, n, p)
+                # form (b): compact rows -- compact_rows() renumbers the rows that occur, rowmap maps them back
+                rowmap = np.unique(ri[sel])
+                if rowmap.size:
+                    renum = np.searchsorted(rowmap, ri[sel]).astype(np.int32)
+                    compact = lib.SparseCOO(int(rowmap.size), cols, renum, ci[sel], Mp.x[sel])
+                    cs = ChunkStream(compact, False, Q, G)
+                    assert cs.stored == int(sel.sum())                           # no dummy entries in a compact band
+                    part = cs.spmv(x, n, p).reshape(rowmap.size, n).astype(np.uint64)
+                    acc[rowmap] = (acc[rowmap] + part) % p                       # store_row<ACC>: y[rowmap[r]] += result
+            assert seen == Mp.nnz                                                # the bands partition the entries
+            assert np.array_equal((partial.sum(axis=0) % p).astype(np.uint32), want), (name, transpose, "partial + combine")
+            assert np.array_equal(acc.astype(np.uint32).ravel(), want), (name, transpose, "accumulate")
