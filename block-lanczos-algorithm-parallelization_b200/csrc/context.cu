@@ -1559,6 +1559,18 @@ int build_bands(blk_ctx *c, SpOp *op, int K, int chunk_len, int64_t count, const
                 int64_t lo, int64_t hi, int64_t cols, bool acc)
 {
         if (K < 2 || hi <= lo || count <= 0) return 0;
+        {
+                // bands are an optimisation: when the device cannot hold them next to what is already resident, the operator
+                // simply stays unbanded (upper bounds: one dummy entry per row and band, the partial blocks, the builder's scratch)
+                size_t free_b = 0, total_b = 0;
+                const double rows = (double)(hi - lo);
+                const double need = 8.0 * ((double)count + rows * K) + (acc ? 4.0 * rows * K : 4.0 * K * rows * c->geo.np) +
+                                    48.0 * (double)count / K + 16.0 * rows;
+                if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || need > 0.85 * (double)free_b) {
+                        cudaGetLastError();
+                        return 0;
+                }
+        }
         std::vector<u32> hc;
         if (count_dimension(c, count, ckey, cols, &hc)) return 1;
         op->band_col.assign((size_t)K + 1, 0);
